@@ -1,0 +1,179 @@
+/* b200timg.h -- C ABI of the B200-native timg hot path.
+ *
+ * Drop-in boundary for hzeller/timg's per-pixel hot path (paths below are relative to
+ * the reference tree):
+ *   scale      ImageScaler::Create/Scale                 src/image-scaler.h:33-39, .cc:75-97
+ *   compose    Framebuffer::AlphaComposeBackground       src/framebuffer.h:103-106, .cc:108-150
+ *   blocks     UnicodeBlockCanvas::Send (+FindBestGlyph, AppendDoubleRow)
+ *                                                         src/unicode-block-canvas.cc:162-403
+ *   sixel      the libsixel calls inside SixelCanvas::Send's encode lambda
+ *                                                         src/sixel-canvas.cc:134-148
+ *   geometry   ImageSource::CalcScaleToFitDisplay        src/image-source.cc:47-153
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All pixel buffers are RGBA8,
+ * row-major, tightly packed (src/framebuffer.h:26-61).  Colours passed as uint32_t are
+ * the four rgba_t bytes in memory order: r | g<<8 | b<<16 | a<<24.
+ *
+ * Every entry point runs hand-written sm_100a CUDA kernels.  There is NO CPU fallback:
+ * if no CUDA device is usable, b200timg_ctx_create fails with B200TIMG_ENODEV and nothing
+ * else can be called.
+ *
+ * Return value: 0 (B200TIMG_OK) or a negative B200TIMG_E* code; b200timg_last_error()
+ * gives a human-readable reason.  The reference's methods return void and cannot fail
+ * (src/terminal-canvas.h:39, src/image-scaler.h:38); the adapters in INTEGRATION.md abort
+ * on a negative code, which is the reference's behaviour on allocation failure too.
+ *
+ * Threading: a ctx is thread-compatible (one caller at a time per ctx), like the
+ * reference's canvases (src/unicode-block-canvas.h:70-79 are plain members).
+ */
+#ifndef B200TIMG_H
+#define B200TIMG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TIMG_OK        0
+#define B200TIMG_EINVAL   (-1)  /* bad argument (null pointer, non-positive size, odd width in quarter mode) */
+#define B200TIMG_ENOMEM   (-2)  /* device or pinned-host allocation failed */
+#define B200TIMG_ECUDA    (-3)  /* a CUDA call or kernel failed; see b200timg_last_error */
+#define B200TIMG_ENOSPC   (-4)  /* caller's output buffer too small; *size holds the needed size */
+#define B200TIMG_ENODEV   (-5)  /* no usable CUDA device (this library has no CPU path) */
+
+/* flags for the block encoders: UnicodeBlockCanvas ctor args, src/unicode-block-canvas.h:38-39 */
+#define B200TIMG_QUARTER   1    /* use_quarter: 2x2 px per cell instead of 1x2 */
+#define B200TIMG_UPPER     2    /* use_upper_half_block (TIMG_USE_UPPER_BLOCK) */
+#define B200TIMG_COLOR8    4    /* use_256_color (--color8) */
+
+/* input colour formats: ImageScaler::ColorFmt, src/image-scaler.h:26-29 */
+#define B200TIMG_FMT_RGBA  0
+#define B200TIMG_FMT_RGB32 1    /* BGRA in memory */
+
+typedef struct b200timg_ctx b200timg_ctx;
+
+/* device: CUDA ordinal.  stream: a cudaStream_t (as void*) to launch on, or NULL for a
+ * stream owned by the ctx. */
+int  b200timg_ctx_create(int device, void *stream, b200timg_ctx **out);
+void b200timg_ctx_destroy(b200timg_ctx *ctx);
+const char *b200timg_last_error(const b200timg_ctx *ctx);
+int  b200timg_version(void);
+/* Number of this library's kernels launched through ctx since creation. */
+uint64_t b200timg_kernel_launches(const b200timg_ctx *ctx);
+
+/* ---- geometry (host only) : ImageSource::CalcScaleToFitDisplay, src/image-source.cc:47-153.
+ * Fields mirror DisplayOptions (src/display-options.h:33-55). Returns 1 if the image needs
+ * scaling, 0 if not, negative on error. */
+typedef struct {
+    int width, height;          /* available pixels */
+    int cell_x_px, cell_y_px;   /* 1x2 half, 2x2 quarter, font cell size for sixel */
+    float width_stretch;
+    int upscale, upscale_integer, fill_width, fill_height;
+} b200timg_fit_opts;
+int b200timg_calc_fit(const b200timg_fit_opts *opts, int img_w, int img_h,
+                      int fit_in_rotated, int *target_w, int *target_h);
+
+/* rgba_t::As256TermColor, src/framebuffer.h:37-52 (host helper, used by tests). */
+int b200timg_as256(uint32_t rgba);
+
+/* ======================= single frame, HOST buffers ==============================
+ * These are the bodies of the reference's methods: they upload, run the kernels,
+ * and download inside the call. */
+
+/* ImageScaler::Scale with the STB scaler's semantics (src/image-scaler.cc:75-97):
+ * Mitchell when shrinking, BOX when enlarging, point-sample copy at scale 1, edge clamp,
+ * alpha-weighted, per axis.  in: iw*ih*4 bytes, out: ow*oh*4 bytes. */
+int b200timg_scale_rgba(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt,
+                        uint8_t *out, int ow, int oh);
+
+/* Framebuffer::AlphaComposeBackground (src/framebuffer.cc:108-150), in place on fb.
+ * has_bg==0 models a null bgcolor_getter ("-b none"); the lazy getter itself stays on
+ * the C++ side: the adapter resolves it only if this frame has a pixel with a<255
+ * (b200timg_has_transparency). */
+int b200timg_compose_bg(b200timg_ctx *ctx, uint8_t *fb, int w, int h, int has_bg,
+                        uint32_t bg, uint32_t pattern, int pattern_w, int pattern_h,
+                        int start_row);
+/* *result = 1 if any pixel at or after start_row has alpha < 255 (the reference's
+ * early-out scan, src/framebuffer.cc:113-117). */
+int b200timg_has_transparency(b200timg_ctx *ctx, const uint8_t *fb, int w, int h,
+                              int start_row, int *result);
+
+/* Worst-case encoded size of one block frame: UnicodeBlockCanvas::RequestBuffers,
+ * src/unicode-block-canvas.cc:405-424. */
+size_t b200timg_blocks_bound(int w, int h);
+
+/* UnicodeBlockCanvas::Send's image bytes (everything after the prefix):
+ * row pairs -> glyph pick -> ANSI bytes, src/unicode-block-canvas.cc:361-399.
+ * prev_fb: NULL for a full frame, else the previous frame (same w,h) for
+ * emit_difference (:344-346; the backing store equals the previous frame).
+ * x_indent_cells: the reference's x after "x /= 2" (:334).
+ * *size == 0 means "nothing changed" (:390-395). */
+int b200timg_blocks_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h,
+                           const uint8_t *prev_fb, int flags, int x_indent_cells,
+                           char *out, size_t cap, size_t *size);
+
+/* Worst-case encoded size of one sixel frame of w x h (h a multiple of 6). */
+size_t b200timg_sixel_bound(int w, int h);
+
+/* What libsixel does inside SixelCanvas::Send (src/sixel-canvas.cc:134-148):
+ * sixel_dither_new(256) + sixel_dither_initialize(RGBA8888, LARGE_LUM,
+ * REP_AVERAGE_COLORS, QUALITY_AUTO) + sixel_encode: 15-bit histogram -> median cut
+ * (<=256) -> Floyd-Steinberg -> DCS q ... ST stream.  fb must already be padded to a
+ * multiple of 6 rows (round_to_sixel, :91-94) and composed; alpha is ignored. */
+int b200timg_sixel_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h,
+                          char *out, size_t cap, size_t *size);
+
+/* ======================= batches, many frames per call ===========================
+ * A batch is n_frames independent source frames of identical geometry, contiguous in
+ * memory (frame f at src + f*src_w*src_h*4).  Each runs
+ *     scale (src -> out_w x out_h) -> compose -> encode
+ * entirely on the device; the scaled framebuffer never leaves it.  Encoded frames are
+ * written back to back into `out`; offsets[f]..offsets[f+1] delimit frame f
+ * (offsets has n_frames+1 entries).  This is the unit the renderer's grid
+ * (src/renderer.cc:103-148) and the animation loops (src/video-source.cc:298-366)
+ * produce one Send() at a time in the reference. */
+typedef struct {
+    int n_frames;
+    int src_w, src_h, src_fmt;
+    int out_w, out_h;           /* from b200timg_calc_fit */
+    /* compose (DisplayOptions: bgcolor_getter result, bg_pattern_color, pattern_size) */
+    int has_bg;
+    uint32_t bg, pattern;
+    int pattern_w, pattern_h;
+    /* block modes */
+    int flags;                  /* B200TIMG_QUARTER | _UPPER | _COLOR8 */
+    int x_indent_cells;
+    int animation;              /* 1: frame f>0 is delta-encoded against frame f-1
+                                   (Send with dy == -height, :344-346); frame 0 is full */
+} b200timg_batch;
+
+/* Device-resident variants: d_src, d_out, d_offsets are DEVICE pointers; nothing crosses
+ * PCIe.  The call is asynchronous on the ctx stream except where it must read a size. */
+int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b,
+                              const uint8_t *d_src, char *d_out, size_t out_cap,
+                              uint64_t *d_offsets);
+int b200timg_sixel_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b,
+                             const uint8_t *d_src, char *d_out, size_t out_cap,
+                             uint64_t *d_offsets);
+
+/* Host variants (the plugin-level call): src/out/offsets are HOST pointers (pinned or
+ * pageable); upload, kernels, and download of exactly the encoded bytes happen inside. */
+int b200timg_blocks_batch(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src,
+                          char *out, size_t out_cap, uint64_t *offsets);
+int b200timg_sixel_batch(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src,
+                         char *out, size_t out_cap, uint64_t *offsets);
+
+/* Device-resident single stages, for tests and for callers that keep frames on the GPU
+ * (e.g. an NVDEC front end).  All pointers are DEVICE pointers. */
+int b200timg_scale_dev(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt,
+                       uint8_t *d_out, int ow, int oh, int n_frames);
+int b200timg_compose_dev(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_frames,
+                         int has_bg, uint32_t bg, uint32_t pattern, int pattern_w,
+                         int pattern_h, int start_row);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TIMG_H */

@@ -135,6 +135,12 @@ class BlockCanvas:
     def send(self, fb, x=0, dy=0, prefix=b""):
         fb = np.ascontiguousarray(fb, dtype=np.uint8)
         h, w = fb.shape[:2]
+        if dy < 0:
+            # Send(): MoveCursorDY(cell_height_for_pixels(dy)) (src/unicode-block-canvas.cc:329,
+            # .h:42-45: (pixels - 1) / 2 with C truncation) -> "ESC[nA" (src/terminal-canvas.cc:66-73)
+            rows = int((dy - 1) / 2)
+            if rows != 0:
+                prefix = prefix + (b"\033[%dA" % -rows if rows < 0 else b"\033[%dB" % rows)
         buf = C.create_string_buffer(lib().orc_blocks_bound(w, h) + len(prefix))
         n = lib().orc_blocks_send(self._h, x, dy, _ptr(fb), w, h, prefix, len(prefix), buf)
         return buf.raw[:n]

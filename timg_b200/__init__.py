@@ -1,0 +1,211 @@
+"""timg_b200 -- Python door onto libb200timg.so (the C ABI in include/b200timg.h).
+
+This module is harness plumbing for tests and bench.py: it loads the in-tree shared
+library with ctypes, declares every symbol of the ABI, and offers small numpy/torch
+conveniences.  The product is the CUDA library; there is no Python or CPU fallback:
+loading fails loudly if the library is missing, and Context() raises if no B200 is
+visible.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200timg.so")
+
+OK, EINVAL, ENOMEM, ECUDA, ENOSPC, ENODEV = 0, -1, -2, -3, -4, -5
+QUARTER, UPPER, COLOR8 = 1, 2, 4
+FMT_RGBA, FMT_RGB32 = 0, 1
+
+u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+
+
+class FitOpts(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("cell_x_px", C.c_int), ("cell_y_px", C.c_int),
+                ("width_stretch", C.c_float), ("upscale", C.c_int), ("upscale_integer", C.c_int),
+                ("fill_width", C.c_int), ("fill_height", C.c_int)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_frames", C.c_int), ("src_w", C.c_int), ("src_h", C.c_int), ("src_fmt", C.c_int),
+                ("out_w", C.c_int), ("out_h", C.c_int), ("has_bg", C.c_int), ("bg", C.c_uint32),
+                ("pattern", C.c_uint32), ("pattern_w", C.c_int), ("pattern_h", C.c_int),
+                ("flags", C.c_int), ("x_indent_cells", C.c_int), ("animation", C.c_int)]
+
+
+# name -> (restype, argtypes); this table IS the list of exported symbols tests check.
+ABI = {
+    "b200timg_version": (C.c_int, []),
+    "b200timg_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200timg_ctx_destroy": (None, [C.c_void_p]),
+    "b200timg_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200timg_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "b200timg_calc_fit": (C.c_int, [C.POINTER(FitOpts), C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200timg_as256": (C.c_int, [C.c_uint32]),
+    "b200timg_scale_rgba": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]),
+    "b200timg_compose_bg": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                      C.c_int, C.c_int, C.c_int]),
+    "b200timg_has_transparency": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "b200timg_blocks_bound": (C.c_size_t, [C.c_int, C.c_int]),
+    "b200timg_blocks_encode": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int,
+                                         C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200timg_sixel_bound": (C.c_size_t, [C.c_int, C.c_int]),
+    "b200timg_sixel_encode": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_char_p, C.c_size_t,
+                                        C.POINTER(C.c_size_t)]),
+    "b200timg_blocks_batch_dev": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p]),
+    "b200timg_sixel_batch_dev": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.c_void_p]),
+    "b200timg_blocks_batch": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
+    "b200timg_sixel_batch": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_void_p]),
+    "b200timg_scale_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_int, C.c_int]),
+    "b200timg_compose_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+                                       C.c_uint32, C.c_int, C.c_int, C.c_int]),
+}
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into timg_b200/libb200timg.so (in-tree)."""
+    subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(timg_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            f = getattr(L, name)          # AttributeError if a declared symbol is not exported
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200timg error {code}: {msg}")
+        self.code = code
+
+
+def rgba_u32(r, g, b, a=255):
+    return (r & 255) | ((g & 255) << 8) | ((b & 255) << 16) | ((a & 255) << 24)
+
+
+def calc_fit(iw, ih, width, height, cell_x=1, cell_y=2, stretch=1.0, upscale=False,
+             upscale_integer=False, fill_width=False, fill_height=False, rotated=False):
+    o = FitOpts(width, height, cell_x, cell_y, stretch, int(upscale), int(upscale_integer),
+                int(fill_width), int(fill_height))
+    tw, th = C.c_int(), C.c_int()
+    r = lib().b200timg_calc_fit(C.byref(o), iw, ih, int(rotated), C.byref(tw), C.byref(th))
+    if r < 0:
+        raise B200Error(r, "calc_fit")
+    return bool(r), tw.value, th.value
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(u8p)
+
+
+class Context:
+    """One b200timg_ctx.  Raises B200Error(ENODEV) when no CUDA device is usable."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        rc = lib().b200timg_ctx_create(device, stream, C.byref(h))
+        if rc != OK:
+            raise B200Error(rc, "ctx_create failed (no usable CUDA device? this library has no CPU path)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200timg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise B200Error(rc, lib().b200timg_last_error(self.h).decode())
+
+    @property
+    def launches(self):
+        return lib().b200timg_kernel_launches(self.h)
+
+    # ---- single-frame host entry points (numpy in / numpy or bytes out)
+    def scale(self, img, ow, oh, fmt=FMT_RGBA):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        ih, iw = img.shape[:2]
+        out = np.empty((oh, ow, 4), np.uint8)
+        self._chk(lib().b200timg_scale_rgba(self.h, _np_ptr(img), iw, ih, fmt, _np_ptr(out), ow, oh))
+        return out
+
+    def compose_bg(self, fb, bg, pattern=0, pw=0, ph=0, start_row=0, has_bg=True):
+        out = np.ascontiguousarray(fb, dtype=np.uint8).copy()
+        h, w = out.shape[:2]
+        self._chk(lib().b200timg_compose_bg(self.h, _np_ptr(out), w, h, int(has_bg), bg, pattern, pw, ph,
+                                            start_row))
+        return out
+
+    def has_transparency(self, fb, start_row=0):
+        fb = np.ascontiguousarray(fb, dtype=np.uint8)
+        h, w = fb.shape[:2]
+        r = C.c_int()
+        self._chk(lib().b200timg_has_transparency(self.h, _np_ptr(fb), w, h, start_row, C.byref(r)))
+        return bool(r.value)
+
+    def blocks_encode(self, fb, prev=None, flags=0, x_indent_cells=0):
+        fb = np.ascontiguousarray(fb, dtype=np.uint8)
+        h, w = fb.shape[:2]
+        cap = lib().b200timg_blocks_bound(w, h) + 64
+        buf = C.create_string_buffer(cap)
+        n = C.c_size_t()
+        pp = None
+        if prev is not None:
+            prev = np.ascontiguousarray(prev, dtype=np.uint8)
+            assert prev.shape == fb.shape
+            pp = _np_ptr(prev)
+        self._chk(lib().b200timg_blocks_encode(self.h, _np_ptr(fb), w, h, pp, flags, x_indent_cells, buf, cap,
+                                               C.byref(n)))
+        return buf.raw[:n.value]
+
+    def sixel_encode(self, fb):
+        fb = np.ascontiguousarray(fb, dtype=np.uint8)
+        h, w = fb.shape[:2]
+        cap = lib().b200timg_sixel_bound(w, h)
+        buf = C.create_string_buffer(cap)
+        n = C.c_size_t()
+        self._chk(lib().b200timg_sixel_encode(self.h, _np_ptr(fb), w, h, buf, cap, C.byref(n)))
+        return buf.raw[:n.value]
+
+    # ---- batches, host buffers (numpy [n,h,w,4]) -> list of bytes
+    def _batch_host(self, fn, frames, b):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        n = frames.shape[0]
+        per = (lib().b200timg_sixel_bound(b.out_w, (b.out_h + 5) // 6 * 6) if fn is lib().b200timg_sixel_batch
+               else lib().b200timg_blocks_bound(b.out_w, b.out_h))
+        cap = per * n + 64
+        out = np.empty(cap, np.uint8)
+        offs = np.zeros(n + 1, np.uint64)
+        self._chk(fn(self.h, C.byref(b), frames.ctypes.data, out.ctypes.data, cap, offs.ctypes.data))
+        return [out[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(n)]
+
+    def blocks_batch(self, frames, b):
+        return self._batch_host(lib().b200timg_blocks_batch, frames, b)
+
+    def sixel_batch(self, frames, b):
+        return self._batch_host(lib().b200timg_sixel_batch, frames, b)

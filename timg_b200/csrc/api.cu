@@ -1,0 +1,343 @@
+// The extern "C" surface declared in include/b200timg.h: context management, host-buffer
+// entry points (upload -> kernels -> download) and the batched pipelines.
+#include <cmath>
+
+#include "common.cuh"
+
+using namespace b200timg;
+
+namespace {
+
+int check_ctx(b200timg_ctx *ctx) { return ctx ? B200TIMG_OK : B200TIMG_EINVAL; }
+
+// Upload helper: pageable or pinned host memory -> device, async on the ctx stream.
+int upload(b200timg_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    B2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B200TIMG_OK;
+}
+int download(b200timg_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    B2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return B200TIMG_OK;
+}
+int sync(b200timg_ctx *ctx) {
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200TIMG_OK;
+}
+
+inline int round_to_sixel(int px) { px += 5; return px - px % 6; }   // src/sixel-canvas.cc:91-94
+
+}  // namespace
+
+extern "C" {
+
+int b200timg_version(void) { return 100; }
+
+int b200timg_ctx_create(int device, void *stream, b200timg_ctx **out) {
+    if (!out) return B200TIMG_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return B200TIMG_ENODEV;   // no CPU fallback by design
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200TIMG_ENODEV; }
+    b200timg_ctx *ctx = new b200timg_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx; return B200TIMG_ECUDA;
+        }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
+    return B200TIMG_OK;
+}
+
+void b200timg_ctx_destroy(b200timg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->in_stage.release(); ctx->fb_scaled.release(); ctx->prev_stage.release();
+    ctx->out_stage.release(); ctx->offsets.release(); ctx->cells.release(); ctx->rows.release();
+    ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release();
+    ctx->pinned.release(); ctx->pinned_io.release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *b200timg_last_error(const b200timg_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+uint64_t b200timg_kernel_launches(const b200timg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- geometry: ImageSource::CalcScaleToFitDisplay, src/image-source.cc:47-153 ------------
+int b200timg_calc_fit(const b200timg_fit_opts *o, int img_w, int img_h, int rotated,
+                      int *target_w, int *target_h) {
+    if (!o || !target_w || !target_h || img_w <= 0 || img_h <= 0) return B200TIMG_EINVAL;
+    int width = o->width, height = o->height;
+    bool fill_w = o->fill_width != 0, fill_h = o->fill_height != 0;
+    float stretch = o->width_stretch;
+    if (rotated) {                                   // :52-56
+        std::swap(width, height);
+        std::swap(fill_w, fill_h);
+        stretch = 1.0f / o->width_stretch;
+    }
+    const float kMaxAccept = 5.0f;                   // :59-63
+    if (stretch > kMaxAccept) stretch = kMaxAccept;
+    if (stretch < 1 / kMaxAccept) stretch = 1 / kMaxAccept;
+    if (stretch > 1.0f) width = (int)((float)width / stretch);      // :65-70
+    else height = (int)((float)height * stretch);
+    const float wfrac = (float)width / (float)img_w;
+    const float hfrac = (float)height / (float)img_h;
+    if (!o->upscale && (fill_h || wfrac > 1.0f) && (fill_w || hfrac > 1.0f)) {   // :75-86
+        *target_w = img_w; *target_h = img_h;
+        if (o->cell_x_px == 2) { *target_w *= 2; return 1; }
+        return 0;
+    }
+    int tw = width, th = height;
+    if (fill_w && fill_h) {
+        const float f = wfrac > hfrac ? wfrac : hfrac;
+        tw = (int)roundf(f * (float)img_w); th = (int)roundf(f * (float)img_h);
+    } else if (fill_h) {
+        tw = (int)roundf(hfrac * (float)img_w);
+    } else if (fill_w) {
+        th = (int)roundf(wfrac * (float)img_h);
+    } else {
+        const float f = wfrac < hfrac ? wfrac : hfrac;
+        tw = (int)roundf(f * (float)img_w); th = (int)roundf(f * (float)img_h);
+    }
+    if (stretch > 1.0f) tw = (int)((float)tw * stretch);            // :120-125
+    else th = (int)((float)th / stretch);
+    if (o->cell_x_px > 0 && o->cell_x_px <= 2 && o->cell_y_px > 0 && o->cell_y_px <= 2) {
+        tw = tw / o->cell_x_px * o->cell_x_px;                      // :129-133
+        th = th / o->cell_y_px * o->cell_y_px;
+    }
+    if (tw <= 0) tw = 1;
+    if (th <= 0) th = 1;
+    if (o->upscale_integer && tw > img_w && th > img_h) {           // :139-150
+        const float aspect = o->cell_x_px == 2 ? 2.0f : 1.0f;
+        const float wf = 1.0f * (float)tw / aspect / (float)img_w;
+        const float hf = 1.0f * (float)th / (float)img_h;
+        const float smaller = wf < hf ? wf : hf;
+        if (smaller > 1.0f) {
+            const double fl = std::floor((double)smaller);
+            tw = (int)((double)aspect * fl * (double)img_w);
+            th = (int)(fl * (double)img_h);
+        }
+    }
+    *target_w = tw; *target_h = th;
+    return (tw != img_w || th != img_h) ? 1 : 0;
+}
+
+int b200timg_as256(uint32_t p) {   // src/framebuffer.h:37-52
+    const uint32_t r = p & 0xff, g = (p >> 8) & 0xff, b = (p >> 16) & 0xff;
+    if (r == g && g == b) return (int)((232 + (r * 23 / 255)) & 0xff);
+    auto cube = [](uint32_t v) -> uint32_t {
+        return v < 47 ? 0 : v < 115 ? 1 : v < 155 ? 2 : v < 195 ? 3 : v < 235 ? 4 : 5;
+    };
+    return (int)(16 + 36 * cube(r) + 6 * cube(g) + cube(b));
+}
+
+// ---- compose ---------------------------------------------------------------------------
+int b200timg_compose_dev(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_frames, int has_bg,
+                         uint32_t bg, uint32_t pattern, int pw, int ph, int start_row) {
+    B2_TRY(check_ctx(ctx));
+    if (!d_fb || w <= 0 || h <= 0 || n_frames <= 0) return ctx->fail(B200TIMG_EINVAL, "compose: bad args");
+    return launch_compose(ctx, d_fb, w, h, n_frames, has_bg, bg, pattern, pw, ph, start_row);
+}
+
+int b200timg_compose_bg(b200timg_ctx *ctx, uint8_t *fb, int w, int h, int has_bg, uint32_t bg,
+                        uint32_t pattern, int pw, int ph, int start_row) {
+    B2_TRY(check_ctx(ctx));
+    if (!fb || w <= 0 || h <= 0) return ctx->fail(B200TIMG_EINVAL, "compose: bad args");
+    const size_t bytes = (size_t)w * h * 4;
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
+    B2_TRY(upload(ctx, ctx->fb_scaled.p, fb, bytes));
+    B2_TRY(launch_compose(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, has_bg, bg, pattern, pw, ph, start_row));
+    B2_TRY(download(ctx, fb, ctx->fb_scaled.p, bytes));
+    return sync(ctx);
+}
+
+int b200timg_has_transparency(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, int start_row,
+                              int *result) {
+    B2_TRY(check_ctx(ctx));
+    if (!fb || !result || w <= 0 || h <= 0) return ctx->fail(B200TIMG_EINVAL, "has_transparency: bad args");
+    const size_t bytes = (size_t)w * h * 4;
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
+    B2_CUDA(ctx, ctx->misc.reserve(64));
+    B2_CUDA(ctx, ctx->pinned.reserve(64));
+    B2_TRY(upload(ctx, ctx->fb_scaled.p, fb, bytes));
+    B2_TRY(launch_has_transparency(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, start_row < 0 ? 0 : start_row,
+                                   ctx->misc.as<int>()));
+    B2_TRY(download(ctx, ctx->pinned.p, ctx->misc.p, sizeof(int)));
+    B2_TRY(sync(ctx));
+    *result = *ctx->pinned.as<int>() ? 1 : 0;
+    return B200TIMG_OK;
+}
+
+// ---- blocks ----------------------------------------------------------------------------
+size_t b200timg_blocks_bound(int w, int h) {   // src/unicode-block-canvas.cc:405-424
+    const size_t max_cell = 2 + 5 + 11 + 1 + 5 + 11 + 1 + 3;
+    const size_t rows = (size_t)(h + 1) / 2;
+    return 9 + rows * (9 + (size_t)w * max_cell + 5);
+}
+
+int b200timg_blocks_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, const uint8_t *prev_fb,
+                           int flags, int x_indent_cells, char *out, size_t cap, size_t *size) {
+    B2_TRY(check_ctx(ctx));
+    if (!fb || !size || w <= 0 || h <= 0 || (!out && cap)) return ctx->fail(B200TIMG_EINVAL, "blocks: bad args");
+    const size_t bytes = (size_t)w * h * 4;
+    const size_t bound = b200timg_blocks_bound(w, h) + 32;
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
+    B2_CUDA(ctx, ctx->out_stage.reserve(bound));
+    B2_CUDA(ctx, ctx->offsets.reserve(2 * sizeof(uint64_t)));
+    B2_CUDA(ctx, ctx->pinned.reserve(64));
+    B2_TRY(upload(ctx, ctx->fb_scaled.p, fb, bytes));
+    if (prev_fb) {
+        B2_CUDA(ctx, ctx->prev_stage.reserve(bytes));
+        B2_TRY(upload(ctx, ctx->prev_stage.p, prev_fb, bytes));
+    }
+    B2_TRY(launch_blocks(ctx, ctx->fb_scaled.as<uint8_t>(), prev_fb ? ctx->prev_stage.as<uint8_t>() : nullptr,
+                         prev_fb ? 1 : 0, w, h, 1, flags, x_indent_cells, ctx->out_stage.as<char>(), bound,
+                         ctx->offsets.as<uint64_t>()));
+    B2_TRY(download(ctx, ctx->pinned.p, ctx->offsets.p, 2 * sizeof(uint64_t)));
+    B2_TRY(sync(ctx));
+    const size_t n = (size_t)ctx->pinned.as<uint64_t>()[1];
+    *size = n;
+    if (n > cap) return ctx->fail(B200TIMG_ENOSPC, "blocks: need %zu bytes, have %zu", n, cap);
+    if (n) { B2_TRY(download(ctx, out, ctx->out_stage.p, n)); B2_TRY(sync(ctx)); }
+    return B200TIMG_OK;
+}
+
+// ---- scale -----------------------------------------------------------------------------
+int b200timg_scale_dev(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out,
+                       int ow, int oh, int n_frames) {
+    B2_TRY(check_ctx(ctx));
+    if (!d_in || !d_out || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0 || n_frames <= 0)
+        return ctx->fail(B200TIMG_EINVAL, "scale: bad args");
+    return launch_scale(ctx, d_in, iw, ih, fmt, d_out, ow, oh, oh, n_frames);
+}
+
+int b200timg_scale_rgba(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt, uint8_t *out,
+                        int ow, int oh) {
+    B2_TRY(check_ctx(ctx));
+    if (!in || !out || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return ctx->fail(B200TIMG_EINVAL, "scale: bad args");
+    const size_t ib = (size_t)iw * ih * 4, ob = (size_t)ow * oh * 4;
+    B2_CUDA(ctx, ctx->in_stage.reserve(ib));
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(ob));
+    B2_TRY(upload(ctx, ctx->in_stage.p, in, ib));
+    B2_TRY(launch_scale(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1));
+    B2_TRY(download(ctx, out, ctx->fb_scaled.p, ob));
+    return sync(ctx);
+}
+
+// ---- sixel -----------------------------------------------------------------------------
+size_t b200timg_sixel_bound(int w, int h) {
+    // header + 256 palette definitions + per band: per colour "#ddd" + w sixels + "$" ; "-"
+    const size_t bands = (size_t)(h + 5) / 6;
+    return 64 + 256 * 20 + bands * (256 * (size_t)(5 + 1) + (size_t)w * 6 + 2) + 8;
+}
+
+int b200timg_sixel_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, char *out, size_t cap,
+                          size_t *size) {
+    B2_TRY(check_ctx(ctx));
+    if (!fb || !size || w <= 0 || h <= 0 || (h % 6) != 0 || (!out && cap))
+        return ctx->fail(B200TIMG_EINVAL, "sixel: bad args (height must be a multiple of 6)");
+    const size_t bytes = (size_t)w * h * 4;
+    const size_t bound = b200timg_sixel_bound(w, h);
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
+    B2_CUDA(ctx, ctx->out_stage.reserve(bound));
+    B2_CUDA(ctx, ctx->offsets.reserve(2 * sizeof(uint64_t)));
+    B2_CUDA(ctx, ctx->pinned.reserve(64));
+    B2_TRY(upload(ctx, ctx->fb_scaled.p, fb, bytes));
+    B2_TRY(launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, ctx->out_stage.as<char>(), bound,
+                        ctx->offsets.as<uint64_t>()));
+    B2_TRY(download(ctx, ctx->pinned.p, ctx->offsets.p, 2 * sizeof(uint64_t)));
+    B2_TRY(sync(ctx));
+    const size_t n = (size_t)ctx->pinned.as<uint64_t>()[1];
+    *size = n;
+    if (n > cap) return ctx->fail(B200TIMG_ENOSPC, "sixel: need %zu bytes, have %zu", n, cap);
+    B2_TRY(download(ctx, out, ctx->out_stage.p, n));
+    return sync(ctx);
+}
+
+// ---- batches -----------------------------------------------------------------------------
+static int validate_batch(b200timg_ctx *ctx, const b200timg_batch *b) {
+    if (!b || b->n_frames <= 0 || b->src_w <= 0 || b->src_h <= 0 || b->out_w <= 0 || b->out_h <= 0)
+        return ctx->fail(B200TIMG_EINVAL, "batch: bad geometry");
+    return B200TIMG_OK;
+}
+
+int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,
+                              char *d_out, size_t out_cap, uint64_t *d_offsets) {
+    B2_TRY(check_ctx(ctx));
+    B2_TRY(validate_batch(ctx, b));
+    if (!d_src || !d_out || !d_offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
+    const size_t fb_bytes = (size_t)b->out_w * b->out_h * 4 * b->n_frames;
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(fb_bytes));
+    uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
+    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, b->out_h, b->n_frames));
+    B2_TRY(launch_compose(ctx, d_fb, b->out_w, b->out_h, b->n_frames, b->has_bg, b->bg, b->pattern,
+                          b->pattern_w, b->pattern_h, 0));
+    return launch_blocks(ctx, d_fb, nullptr, b->animation ? 2 : 0, b->out_w, b->out_h, b->n_frames, b->flags,
+                         b->x_indent_cells, d_out, out_cap, d_offsets);
+}
+
+int b200timg_sixel_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,
+                             char *d_out, size_t out_cap, uint64_t *d_offsets) {
+    B2_TRY(check_ctx(ctx));
+    B2_TRY(validate_batch(ctx, b));
+    if (!d_src || !d_out || !d_offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
+    // SixelCanvas::Send (src/sixel-canvas.cc:109-120): pad to a multiple of 6 rows with
+    // transparent pixels, compose the background into the pad strip only, keep the rest.
+    const int hp = round_to_sixel(b->out_h);
+    const size_t frame_bytes = (size_t)b->out_w * hp * 4;
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(frame_bytes * b->n_frames));
+    uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
+    if (hp != b->out_h) B2_CUDA(ctx, cudaMemsetAsync(d_fb, 0, frame_bytes * b->n_frames, ctx->stream));
+    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, hp, b->n_frames));
+    // sources compose the image itself first (e.g. src/stb-image-source.cc:56-60) ...
+    // (start_row 0 over the real rows; the pad rows are transparent so they get bg too,
+    //  which is exactly what the canvas' own start_row=h call (:115-118) produces.)
+    B2_TRY(launch_compose(ctx, d_fb, b->out_w, hp, b->n_frames, b->has_bg, b->bg, b->pattern, b->pattern_w,
+                          b->pattern_h, 0));
+    return launch_sixel(ctx, d_fb, b->out_w, hp, b->n_frames, d_out, out_cap, d_offsets);
+}
+
+static int batch_host(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,
+                      size_t out_cap, uint64_t *offsets, bool sixel) {
+    B2_TRY(check_ctx(ctx));
+    B2_TRY(validate_batch(ctx, b));
+    if (!src || !out || !offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
+    const size_t in_bytes = (size_t)b->src_w * b->src_h * 4 * b->n_frames;
+    const size_t per = sixel ? b200timg_sixel_bound(b->out_w, round_to_sixel(b->out_h))
+                             : b200timg_blocks_bound(b->out_w, b->out_h);
+    const size_t bound = per * b->n_frames + 64;
+    B2_CUDA(ctx, ctx->in_stage.reserve(in_bytes));
+    B2_CUDA(ctx, ctx->out_stage.reserve(bound));
+    B2_CUDA(ctx, ctx->offsets.reserve((size_t)(b->n_frames + 1) * sizeof(uint64_t)));
+    B2_TRY(upload(ctx, ctx->in_stage.p, src, in_bytes));
+    int rc = sixel ? b200timg_sixel_batch_dev(ctx, b, ctx->in_stage.as<uint8_t>(), ctx->out_stage.as<char>(), bound,
+                                              ctx->offsets.as<uint64_t>())
+                   : b200timg_blocks_batch_dev(ctx, b, ctx->in_stage.as<uint8_t>(), ctx->out_stage.as<char>(), bound,
+                                               ctx->offsets.as<uint64_t>());
+    if (rc != B200TIMG_OK) return rc;
+    B2_TRY(download(ctx, offsets, ctx->offsets.p, (size_t)(b->n_frames + 1) * sizeof(uint64_t)));
+    B2_TRY(sync(ctx));
+    const size_t total = (size_t)offsets[b->n_frames];
+    if (total > out_cap) return ctx->fail(B200TIMG_ENOSPC, "batch: need %zu bytes, have %zu", total, out_cap);
+    if (total) { B2_TRY(download(ctx, out, ctx->out_stage.p, total)); B2_TRY(sync(ctx)); }
+    return B200TIMG_OK;
+}
+
+int b200timg_blocks_batch(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,
+                          size_t out_cap, uint64_t *offsets) {
+    return batch_host(ctx, b, src, out, out_cap, offsets, false);
+}
+int b200timg_sixel_batch(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,
+                         size_t out_cap, uint64_t *offsets) {
+    return batch_host(ctx, b, src, out, out_cap, offsets, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// Shared internals of libb200timg: context, scratch arena, error plumbing and the
+// strict-IEEE float helpers every bit-exact kernel uses.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200timg.h"
+
+namespace b200timg {
+
+// A grow-only device buffer (never shrinks; freed with the ctx).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {   // pinned staging
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace b200timg
+
+struct b200timg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    char err[512] = {0};
+
+    // scratch, grown on demand
+    b200timg::DevBuf in_stage;     // uploaded source frames (host entry points)
+    b200timg::DevBuf fb_scaled;    // scaled (+padded) RGBA framebuffers of a batch
+    b200timg::DevBuf prev_stage;   // previous frame for single-frame delta encode
+    b200timg::DevBuf out_stage;    // encoded bytes (host entry points)
+    b200timg::DevBuf offsets;      // uint64 [n+1]
+    b200timg::DevBuf cells;        // per-cell records of the block encoder
+    b200timg::DevBuf rows;         // per-rowpair records
+    b200timg::DevBuf tables;       // resampler coefficient tables
+    b200timg::DevBuf sixel_work;   // palettes, LUTs, index planes, band tables
+    b200timg::DevBuf misc;         // small flags / sizes
+    b200timg::HostBuf pinned;      // staging for sizes / offsets
+    b200timg::HostBuf pinned_io;   // staging for pageable payloads
+
+    int fail(int code, const char *fmt, ...) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(err, sizeof err, fmt, ap);
+        va_end(ap);
+        return code;
+    }
+};
+
+#define B2_CUDA(ctx, call)                                                         \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess)                                                    \
+            return (ctx)->fail(e__ == cudaErrorMemoryAllocation ? B200TIMG_ENOMEM  \
+                                                                : B200TIMG_ECUDA,  \
+                               "%s:%d %s -> %s", __FILE__, __LINE__, #call,        \
+                               cudaGetErrorString(e__));                           \
+    } while (0)
+
+#define B2_LAUNCH_CHECK(ctx)                                                       \
+    do {                                                                           \
+        (ctx)->launches++;                                                         \
+        cudaError_t e__ = cudaGetLastError();                                      \
+        if (e__ != cudaSuccess)                                                    \
+            return (ctx)->fail(B200TIMG_ECUDA, "%s:%d kernel launch -> %s",        \
+                               __FILE__, __LINE__, cudaGetErrorString(e__));       \
+    } while (0)
+
+#define B2_TRY(expr)                          \
+    do {                                      \
+        int rc__ = (expr);                    \
+        if (rc__ != B200TIMG_OK) return rc__; \
+    } while (0)
+
+namespace b200timg {
+
+// ---- strict IEEE-754 single precision, never contracted into FMA ------------------
+// The reference is compiled for baseline x86-64 (SSE2, no FMA): every * and + rounds
+// separately.  These intrinsics map to single SASS FMUL/FADD/MUFU+fixup and are never
+// fused by ptxas, independent of -fmad.
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+// LinearColor::gamma (src/framebuffer.h:169-172): sqrt, saturate at 255, truncate.
+__device__ __forceinline__ uint32_t ungamma(float v) {
+    const float s = fsqrt(v);
+    return (s > 255.0f) ? 255u : __float2uint_rz(s);
+}
+
+struct __align__(4) px4 { uint8_t r, g, b, a; };
+
+__device__ __forceinline__ uint32_t pack_rgba(uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+
+// per-stage launchers (defined in the .cu files); all device pointers
+int launch_compose(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_frames, int has_bg,
+                   uint32_t bg, uint32_t pattern, int pw, int ph, int start_row);
+int launch_has_transparency(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h,
+                            int start_row, int *d_flag);
+// Block encode of n frames of w x h at d_fb (frame stride w*h*4).  prev_mode: 0 none,
+// 1 = explicit d_prev (single frame), 2 = animation (frame f vs f-1, frame 0 full).
+int launch_blocks(b200timg_ctx *ctx, const uint8_t *d_fb, const uint8_t *d_prev, int prev_mode,
+                  int w, int h, int n_frames, int flags, int x_indent, char *d_out,
+                  size_t out_cap, uint64_t *d_offsets);
+int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out,
+                 int ow, int oh, int out_frame_rows, int n_frames);
+int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
+                 size_t out_cap, uint64_t *d_offsets);
+
+}  // namespace b200timg
