@@ -173,6 +173,16 @@ int b200timg_compose_dev(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_f
                          int has_bg, uint32_t bg, uint32_t pattern, int pattern_w,
                          int pattern_h, int start_row);
 
+/* Host-only introspection of the resampling plan behind b200timg_scale_* (no GPU needed):
+ * the per-axis contributor tables and the pass order that reproduce the reference scaler's
+ * arithmetic (third_party/stb/stb_image_resize2.h:3267-3635, 6859-6905).  axis 0 = horizontal,
+ * 1 = vertical.  first/count/lead have out_w (or out_h) entries, coeff has entries*widest.
+ * flags: bit0 vertical pass first, bit1 plain copy (both axes at scale 1), bit2 horizontal taps
+ * use a single accumulator.  Any output pointer may be NULL. */
+int b200timg_resample_plan(int in_w, int in_h, int out_w, int out_h, int axis, int *widest,
+                           int *flags, int32_t *first, int32_t *count, int32_t *lead,
+                           float *coeff, size_t coeff_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,10 @@ def lib():
         _sig(L, "orc_blocks_bound", C.c_long, [C.c_int, C.c_int])
         _sig(L, "orc_blocks_send", C.c_long, [C.c_void_p, C.c_int, C.c_int, u8p, C.c_int, C.c_int,
                                               C.c_char_p, C.c_int, C.c_char_p])
+        _sig(L, "orc_stb_resize", C.c_int, [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int,
+                                            C.POINTER(C.c_int)])
+        _sig(L, "orc_stb_plan", C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p])
         _ORC = L
     return _ORC
 
@@ -124,6 +128,29 @@ def calc_fit(iw, ih, width, height, cell_x=1, cell_y=2, stretch=1.0, upscale=Fal
     r = f(iw, ih, width, height, cell_x, cell_y, stretch, int(upscale), int(upscale_integer),
           int(fill_width), int(fill_height), int(rotated), C.byref(tw), C.byref(th))
     return bool(r), tw.value, th.value
+
+
+def stb_resize(img, ow, oh, fmt=0, want_info=False):
+    """Restatement of ImageScaler::Scale (STB build). info = [vertical_first, h_widest, v_widest, channels]."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    ih, iw = img.shape[:2]
+    out = np.empty((oh, ow, 4), np.uint8)
+    info = (C.c_int * 4)()
+    rc = lib().orc_stb_resize(_ptr(img), iw, ih, fmt, _ptr(out), ow, oh, info)
+    assert rc == 0, rc
+    return (out, list(info)) if want_info else out
+
+
+def stb_plan(iw, ih, ow, oh, axis):
+    n = ow if axis == 0 else oh
+    widest, flags = C.c_int(), C.c_int()
+    assert lib().orc_stb_plan(iw, ih, ow, oh, axis, C.byref(widest), C.byref(flags), None, None, None, None) == 0
+    first, count, lead = (np.zeros(n, np.int32) for _ in range(3))
+    coeff = np.zeros(n * widest.value, np.float32)
+    assert lib().orc_stb_plan(iw, ih, ow, oh, axis, None, None, first.ctypes.data, count.ctypes.data,
+                              lead.ctypes.data, coeff.ctypes.data) == 0
+    return dict(widest=widest.value, flags=flags.value, first=first, count=count, lead=lead,
+                coeff=coeff.reshape(n, widest.value))
 
 
 class BlockCanvas:

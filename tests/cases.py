@@ -152,3 +152,23 @@ def run_block_case(make_canvas, case):
     for i, fr in enumerate(case["frames"]):
         outs.append(cv.send(fr, case["x"], 0 if i == 0 else case["dy"]))
     return outs
+
+
+def scale_cases():
+    """(name, img, ow, oh, fmt) for ImageScaler::Scale parity (SURVEY App. C 'scaler' row)."""
+    out = []
+    geos = [("c1_640x480_to_67x50", 640, 480, 67, 50), ("identity", 61, 47, 61, 47), ("up2", 40, 30, 80, 60),
+            ("up3", 21, 17, 63, 51), ("up_nonint", 37, 23, 80, 51), ("down_nonint", 200, 150, 141, 106),
+            ("down_h_only", 200, 60, 77, 60), ("down_v_only", 120, 200, 120, 33), ("to_1x1", 17, 9, 1, 1),
+            ("to_1xN", 50, 40, 1, 13), ("c3_ratio_1080p", 384, 216, 64, 18), ("c2_ratio_45_64", 256, 144, 180, 101),
+            ("extreme_down", 1000, 30, 20, 3), ("mixed_up_down", 30, 300, 90, 40), ("tall_scatter", 12, 400, 12, 9)]
+    for name, iw, ih, ow, oh in geos:
+        for kind in ("noisea", "photo"):
+            img = synth.frame_np(iw * 31 + ih, iw, ih, kind)
+            if kind == "noisea":
+                img[: ih // 3, :, 3] = 0                   # alpha=0 region keeps RGB (fancy alpha)
+            out.append((f"{name}_{kind}", img, ow, oh, 0))
+    img = synth.frame_np(99, 90, 70, "alpha")
+    out.append(("bgra_down", img, 45, 31, 1))
+    out.append(("bgra_identity", img, 90, 70, 1))
+    return out

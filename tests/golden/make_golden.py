@@ -29,6 +29,10 @@ def main():
     for name, fb, kw in cases.compose_cases():
         comp[name] = oracle.ref_compose_bg(fb, **kw)
     np.savez_compressed(os.path.join(HERE, "compose.npz"), **comp)
+    sc = {}
+    for name, img, ow, oh, fmt in cases.scale_cases():
+        sc[name] = oracle.ref_scale(img, ow, oh, fmt)
+    np.savez_compressed(os.path.join(HERE, "scale.npz"), **sc)
     fit = []
     rng = np.random.default_rng(5)
     for _ in range(400):

@@ -68,6 +68,8 @@ ABI = {
                                      C.c_int, C.c_int]),
     "b200timg_compose_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                        C.c_uint32, C.c_int, C.c_int, C.c_int]),
+    "b200timg_resample_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }
 
 _lib = None
@@ -113,6 +115,24 @@ def calc_fit(iw, ih, width, height, cell_x=1, cell_y=2, stretch=1.0, upscale=Fal
     if r < 0:
         raise B200Error(r, "calc_fit")
     return bool(r), tw.value, th.value
+
+
+def resample_plan(iw, ih, ow, oh, axis):
+    """Host-side resampling plan of one axis as numpy arrays (see include/b200timg.h)."""
+    n = ow if axis == 0 else oh
+    widest, flags = C.c_int(), C.c_int()
+    rc = lib().b200timg_resample_plan(iw, ih, ow, oh, axis, C.byref(widest), C.byref(flags), None, None, None,
+                                      None, 1 << 62)
+    if rc != OK:
+        raise B200Error(rc, "resample_plan")
+    first, count, lead = (np.zeros(n, np.int32) for _ in range(3))
+    coeff = np.zeros(n * widest.value, np.float32)
+    rc = lib().b200timg_resample_plan(iw, ih, ow, oh, axis, None, None, first.ctypes.data, count.ctypes.data,
+                                      lead.ctypes.data, coeff.ctypes.data, coeff.size)
+    if rc != OK:
+        raise B200Error(rc, "resample_plan")
+    return dict(widest=widest.value, flags=flags.value, first=first, count=count, lead=lead,
+                coeff=coeff.reshape(n, widest.value))
 
 
 def _np_ptr(a):

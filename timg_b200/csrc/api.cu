@@ -65,6 +65,7 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release();
     ctx->pinned.release(); ctx->pinned_io.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->plan) free_plan(ctx->plan);
     delete ctx;
 }
 

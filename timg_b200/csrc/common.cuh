@@ -49,8 +49,12 @@ struct HostBuf {   // pinned staging
 
 }  // namespace b200timg
 
+namespace b200timg { struct ResamplePlan; void free_plan(ResamplePlan *); }
+
 struct b200timg_ctx {
     int device = 0;
+    b200timg::ResamplePlan *plan = nullptr;   // cached resampling tables (host copy) ...
+    int plan_key[4] = {0, 0, 0, 0};           // ... for this iw, ih, ow, oh (device copy in `tables`)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
