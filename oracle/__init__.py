@@ -61,6 +61,11 @@ def lib():
                                             C.POINTER(C.c_int)])
         _sig(L, "orc_stb_plan", C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p])
+        _sig(L, "orc_sixel_encode", C.c_long, [u8p, C.c_int, C.c_int, C.c_char_p, C.c_long, u8p,
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int), u8p])
+        _sig(L, "orc_sixel_palette", C.c_int, [u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_int)])
+        _sig(L, "orc_sixel_decode", C.c_int, [C.c_char_p, C.c_long, u8p, C.c_long, C.POINTER(C.c_int),
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int)])
         _ORC = L
     return _ORC
 
@@ -151,6 +156,68 @@ def stb_plan(iw, ih, ow, oh, axis):
                               lead.ctypes.data, coeff.ctypes.data) == 0
     return dict(widest=widest.value, flags=flags.value, first=first, count=count, lead=lead,
                 coeff=coeff.reshape(n, widest.value))
+
+
+def sixel_encode(fb, want_details=False):
+    """Restatement of libsixel's encode for the reference's call sequence (PARITY UNPINNED)."""
+    fb = np.ascontiguousarray(fb, dtype=np.uint8)
+    h, w = fb.shape[:2]
+    cap = 1024 + w * h * 5 + 256 * 24        # the reference's own bound, src/sixel-canvas.cc:123
+    buf = C.create_string_buffer(cap)
+    pal = np.zeros((256, 3), np.uint8)
+    idx = np.zeros((h, w), np.uint8)
+    nc, oc = C.c_int(), C.c_int()
+    n = lib().orc_sixel_encode(_ptr(fb), w, h, buf, cap, _ptr(pal), C.byref(nc), C.byref(oc), _ptr(idx))
+    assert n > 0, n
+    if want_details:
+        return buf.raw[:n], dict(palette=pal[:nc.value], ncolors=nc.value, origcolors=oc.value, index=idx)
+    return buf.raw[:n]
+
+
+def sixel_palette(fb):
+    fb = np.ascontiguousarray(fb, dtype=np.uint8)
+    h, w = fb.shape[:2]
+    pal = np.zeros((256, 3), np.uint8)
+    oc = C.c_int()
+    n = lib().orc_sixel_palette(_ptr(fb), w, h, _ptr(pal), C.byref(oc))
+    return pal[:n], oc.value
+
+
+def sixel_decode(data, max_px=1 << 26):
+    """Decode a DCS sixel stream -> (HxWx3 uint8, colours used)."""
+    w, h, used = C.c_int(), C.c_int(), C.c_int()
+    out = np.zeros(max_px * 3, np.uint8)
+    rc = lib().orc_sixel_decode(data, len(data), _ptr(out), max_px, C.byref(w), C.byref(h), C.byref(used))
+    if rc != 0:
+        raise ValueError(f"malformed sixel stream ({rc})")
+    return out[: w.value * h.value * 3].reshape(h.value, w.value, 3).copy(), used.value
+
+
+def rgb_to_lab(rgb):
+    """sRGB (D65) -> CIE L*a*b*, float64, for CIE76 delta-E."""
+    c = rgb.astype(np.float64) / 255.0
+    c = np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+    m = np.array([[0.4124564, 0.3575761, 0.1804375], [0.2126729, 0.7151522, 0.0721750],
+                  [0.0193339, 0.1191920, 0.9503041]])
+    xyz = c @ m.T / np.array([0.95047, 1.0, 1.08883])
+    f = np.where(xyz > 216 / 24389, np.cbrt(xyz), (24389 / 27 * xyz + 16) / 116)
+    return np.stack([116 * f[..., 1] - 16, 500 * (f[..., 0] - f[..., 1]), 200 * (f[..., 1] - f[..., 2])], -1)
+
+
+def mean_delta_e(a_rgb, b_rgb, blur=0):
+    """Mean CIE76 delta-E between two RGB images; blur>0 box-filters both first (dither noise
+    averages out over a (2*blur+1)^2 neighbourhood, which is how a dithered image is perceived)."""
+    a, b = a_rgb.astype(np.float64), b_rgb.astype(np.float64)
+    if blur:
+        k = 2 * blur + 1
+
+        def box(x):
+            p = np.pad(x, ((blur, blur), (blur, blur), (0, 0)), mode="edge")
+            cs = np.cumsum(np.cumsum(np.pad(p, ((1, 0), (1, 0), (0, 0))), 0), 1)
+            return (cs[k:, k:] - cs[:-k, k:] - cs[k:, :-k] + cs[:-k, :-k]) / (k * k)
+        a, b = box(a), box(b)
+    d = rgb_to_lab(a) - rgb_to_lab(b)
+    return float(np.sqrt((d ** 2).sum(-1)).mean())
 
 
 class BlockCanvas:
