@@ -173,6 +173,12 @@ int b200timg_compose_dev(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_f
                          int has_bg, uint32_t bg, uint32_t pattern, int pattern_w,
                          int pattern_h, int start_row);
 
+/* Introspection for tests: after b200timg_sixel_encode, the palette (256 words r|g<<8|b<<16),
+ * counts[0] = palette entries in use, counts[1] = occupied 15-bit histogram cells, and the
+ * palette-index plane (w*h bytes) of that frame.  Any pointer may be NULL. */
+int b200timg_sixel_debug(b200timg_ctx *ctx, uint32_t *palette, uint32_t *counts, uint8_t *index,
+                         size_t index_bytes);
+
 /* Host-only introspection of the resampling plan behind b200timg_scale_* (no GPU needed):
  * the per-axis contributor tables and the pass order that reproduce the reference scaler's
  * arithmetic (third_party/stb/stb_image_resize2.h:3267-3635, 6859-6905).  axis 0 = horizontal,

@@ -61,9 +61,9 @@ def lib():
                                             C.POINTER(C.c_int)])
         _sig(L, "orc_stb_plan", C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p])
-        _sig(L, "orc_sixel_encode", C.c_long, [u8p, C.c_int, C.c_int, C.c_char_p, C.c_long, u8p,
+        _sig(L, "orc_sixel_encode", C.c_long, [u8p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_long, u8p,
                                               C.POINTER(C.c_int), C.POINTER(C.c_int), u8p])
-        _sig(L, "orc_sixel_palette", C.c_int, [u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_int)])
+        _sig(L, "orc_sixel_palette", C.c_int, [u8p, C.c_int, C.c_int, C.c_int, u8p, C.POINTER(C.c_int)])
         _sig(L, "orc_sixel_decode", C.c_int, [C.c_char_p, C.c_long, u8p, C.c_long, C.POINTER(C.c_int),
                                               C.POINTER(C.c_int), C.POINTER(C.c_int)])
         _ORC = L
@@ -158,8 +158,9 @@ def stb_plan(iw, ih, ow, oh, axis):
                 coeff=coeff.reshape(n, widest.value))
 
 
-def sixel_encode(fb, want_details=False):
-    """Restatement of libsixel's encode for the reference's call sequence (PARITY UNPINNED)."""
+def sixel_encode(fb, want_details=False, mode=0):
+    """Restatement of libsixel's encode for the reference's call sequence (PARITY UNPINNED).
+    mode 0 = libsixel-faithful; mode 1 = order-free "device semantics" (see oracle/sixel_oracle.c)."""
     fb = np.ascontiguousarray(fb, dtype=np.uint8)
     h, w = fb.shape[:2]
     cap = 1024 + w * h * 5 + 256 * 24        # the reference's own bound, src/sixel-canvas.cc:123
@@ -167,19 +168,19 @@ def sixel_encode(fb, want_details=False):
     pal = np.zeros((256, 3), np.uint8)
     idx = np.zeros((h, w), np.uint8)
     nc, oc = C.c_int(), C.c_int()
-    n = lib().orc_sixel_encode(_ptr(fb), w, h, buf, cap, _ptr(pal), C.byref(nc), C.byref(oc), _ptr(idx))
+    n = lib().orc_sixel_encode(_ptr(fb), w, h, mode, buf, cap, _ptr(pal), C.byref(nc), C.byref(oc), _ptr(idx))
     assert n > 0, n
     if want_details:
         return buf.raw[:n], dict(palette=pal[:nc.value], ncolors=nc.value, origcolors=oc.value, index=idx)
     return buf.raw[:n]
 
 
-def sixel_palette(fb):
+def sixel_palette(fb, mode=0):
     fb = np.ascontiguousarray(fb, dtype=np.uint8)
     h, w = fb.shape[:2]
     pal = np.zeros((256, 3), np.uint8)
     oc = C.c_int()
-    n = lib().orc_sixel_palette(_ptr(fb), w, h, _ptr(pal), C.byref(oc))
+    n = lib().orc_sixel_palette(_ptr(fb), w, h, mode, _ptr(pal), C.byref(oc))
     return pal[:n], oc.value
 
 

@@ -50,7 +50,12 @@ static void sort_boxes(box_t *b, int n) {           /* sumcompare: descending by
 
 /* quant.c sixel_quant_make_palette -> computeColorMapFromInput.  rgb: w*h*3 bytes.
  * Returns number of palette entries (<=256); *origcolors = occupied buckets. */
-static int make_palette(const uint8_t *rgb, long npix, uint8_t *palette, int *origcolors) {
+/* mode 0: libsixel-faithful.  mode 1: "device semantics" -- the two places where libsixel's result
+ * depends on raster order are replaced by order-free rules so that a parallel implementation can
+ * be compared bit for bit: (a) the histogram table starts in bucket-index order instead of
+ * first-seen order (only changes how ties sort), (b) the nearest-colour memo of a 15-bit cell is
+ * the nearest palette entry to the cell CENTRE instead of to whichever pixel hit the cell first. */
+static int make_palette(const uint8_t *rgb, long npix, uint8_t *palette, int *origcolors, int mode) {
     const unsigned depth = 3, reqcolors = 256, max_sample = 18383;      /* QUALITY_AUTO -> LOW */
     const unsigned long length = (unsigned long)npix * depth;
     unsigned long step = length / depth / max_sample * depth;
@@ -65,6 +70,7 @@ static int make_palette(const uint8_t *rgb, long npix, uint8_t *palette, int *or
         if (hist[b] < 65535) hist[b]++;
     }
     hcolor_t *tab = (hcolor_t *)malloc((size_t)(nref ? nref : 1) * sizeof *tab);
+    if (mode == 1) { nref = 0; for (unsigned b = 0; b < (1u << 15); b++) if (hist[b]) refmap[nref++] = (uint16_t)b; }
     for (int i = 0; i < nref; i++) {                 /* first-seen order; colour = 5-bit value << 3 */
         const unsigned b = refmap[i];
         tab[i].c[0] = (uint8_t)(((b >> 10) & 31) << 3);
@@ -136,8 +142,21 @@ static void fs_add(uint8_t *data, long pos, int error, int num) {       /* quant
 
 /* quant.c sixel_quant_apply_palette (foptimize=1, foptimize_palette=0, complexion=1) */
 static void apply_palette(uint8_t *rgb, int w, int h, const uint8_t *palette, int ncolors, int diffuse,
-                          uint8_t *index) {
+                          uint8_t *index, int mode) {
     uint16_t *cache = (uint16_t *)calloc(1 << 15, sizeof(uint16_t));
+    if (mode == 1)
+        for (unsigned b = 0; b < (1u << 15); b++) {
+            const int c[3] = {(int)(((b >> 10) & 31) << 3 | 4), (int)(((b >> 5) & 31) << 3 | 4), (int)((b & 31) << 3 | 4)};
+            int diff = INT_MAX, ci = -1;
+            for (int i = 0; i < ncolors; i++) {
+                int d = 0, r;
+                r = c[0] - palette[i * 3 + 0]; d += r * r;
+                r = c[1] - palette[i * 3 + 1]; d += r * r;
+                r = c[2] - palette[i * 3 + 2]; d += r * r;
+                if (d < diff) { diff = d; ci = i; }
+            }
+            cache[b] = (uint16_t)(ci + 1);
+        }
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             const long pos = (long)y * w + x;
@@ -264,17 +283,17 @@ static long encode_body(const uint8_t *index, int w, int h, const uint8_t *palet
 /* RGBA8 in (alpha dropped: sixel_helper_normalize_pixelformat RGBA8888 -> RGB888).
  * palette_out: 768 bytes or NULL; index_out: w*h bytes or NULL.
  * Returns bytes written, or -1 if cap was too small. */
-long orc_sixel_encode(const uint8_t *rgba, int w, int h, char *out, long cap, uint8_t *palette_out,
+long orc_sixel_encode(const uint8_t *rgba, int w, int h, int mode, char *out, long cap, uint8_t *palette_out,
                       int *ncolors_out, int *origcolors_out, uint8_t *index_out) {
     const long npix = (long)w * h;
     uint8_t *rgb = (uint8_t *)malloc((size_t)npix * 3);
     for (long i = 0; i < npix; i++) { rgb[3 * i] = rgba[4 * i]; rgb[3 * i + 1] = rgba[4 * i + 1]; rgb[3 * i + 2] = rgba[4 * i + 2]; }
     uint8_t palette[768]; int orig = 0;
-    const int ncolors = make_palette(rgb, npix, palette, &orig);
+    const int ncolors = make_palette(rgb, npix, palette, &orig, mode);
     /* sixel_dither_initialize: origcolors <= reqcolors switches diffusion off */
     const int diffuse = orig > 256;
     uint8_t *index = (uint8_t *)malloc((size_t)npix);
-    apply_palette(rgb, w, h, palette, ncolors, diffuse, index);
+    apply_palette(rgb, w, h, palette, ncolors, diffuse, index, mode);
     const long n = encode_body(index, w, h, palette, ncolors, out, cap);
     if (palette_out) memcpy(palette_out, palette, 768);
     if (ncolors_out) *ncolors_out = ncolors;
@@ -285,12 +304,12 @@ long orc_sixel_encode(const uint8_t *rgba, int w, int h, char *out, long cap, ui
 }
 
 /* Palette only (for comparing the device median cut with the restatement). */
-int orc_sixel_palette(const uint8_t *rgba, int w, int h, uint8_t *palette_out, int *origcolors_out) {
+int orc_sixel_palette(const uint8_t *rgba, int w, int h, int mode, uint8_t *palette_out, int *origcolors_out) {
     const long npix = (long)w * h;
     uint8_t *rgb = (uint8_t *)malloc((size_t)npix * 3);
     for (long i = 0; i < npix; i++) { rgb[3 * i] = rgba[4 * i]; rgb[3 * i + 1] = rgba[4 * i + 1]; rgb[3 * i + 2] = rgba[4 * i + 2]; }
     int orig = 0;
-    const int n = make_palette(rgb, npix, palette_out, &orig);
+    const int n = make_palette(rgb, npix, palette_out, &orig, mode);
     if (origcolors_out) *origcolors_out = orig;
     free(rgb);
     return n;

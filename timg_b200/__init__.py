@@ -68,6 +68,7 @@ ABI = {
                                      C.c_int, C.c_int]),
     "b200timg_compose_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                        C.c_uint32, C.c_int, C.c_int, C.c_int]),
+    "b200timg_sixel_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200timg_resample_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
 }
@@ -206,19 +207,34 @@ class Context:
     def sixel_encode(self, fb):
         fb = np.ascontiguousarray(fb, dtype=np.uint8)
         h, w = fb.shape[:2]
-        cap = lib().b200timg_sixel_bound(w, h)
+        cap = 4096 + 6 * w * h
         buf = C.create_string_buffer(cap)
         n = C.c_size_t()
-        self._chk(lib().b200timg_sixel_encode(self.h, _np_ptr(fb), w, h, buf, cap, C.byref(n)))
+        rc = lib().b200timg_sixel_encode(self.h, _np_ptr(fb), w, h, buf, cap, C.byref(n))
+        if rc == ENOSPC:                       # sized exactly by the library before anything is written
+            cap = n.value
+            buf = C.create_string_buffer(cap)
+            rc = lib().b200timg_sixel_encode(self.h, _np_ptr(fb), w, h, buf, cap, C.byref(n))
+        self._chk(rc)
         return buf.raw[:n.value]
 
+    def sixel_debug(self, w, h):
+        """(palette[n,3] uint8, origcolors, index[h,w]) of the last sixel_encode call."""
+        pal = np.zeros(256, np.uint32)
+        cnt = np.zeros(2, np.uint32)
+        idx = np.zeros((h, w), np.uint8)
+        self._chk(lib().b200timg_sixel_debug(self.h, pal.ctypes.data, cnt.ctypes.data, idx.ctypes.data, idx.size))
+        rgb = np.stack([pal & 255, (pal >> 8) & 255, (pal >> 16) & 255], -1).astype(np.uint8)
+        return rgb[: int(cnt[0])], int(cnt[1]), idx
+
     # ---- batches, host buffers (numpy [n,h,w,4]) -> list of bytes
-    def _batch_host(self, fn, frames, b):
+    def _batch_host(self, fn, frames, b, sixel=False):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         n = frames.shape[0]
-        per = (lib().b200timg_sixel_bound(b.out_w, (b.out_h + 5) // 6 * 6) if fn is lib().b200timg_sixel_batch
-               else lib().b200timg_blocks_bound(b.out_w, b.out_h))
-        cap = per * n + 64
+        if sixel:
+            cap = n * (4096 + 6 * b.out_w * (b.out_h + 5))      # far above typical (~1 B/px); ENOSPC reports the need
+        else:
+            cap = lib().b200timg_blocks_bound(b.out_w, b.out_h) * n + 64
         out = np.empty(cap, np.uint8)
         offs = np.zeros(n + 1, np.uint64)
         self._chk(fn(self.h, C.byref(b), frames.ctypes.data, out.ctypes.data, cap, offs.ctypes.data))
@@ -228,4 +244,4 @@ class Context:
         return self._batch_host(lib().b200timg_blocks_batch, frames, b)
 
     def sixel_batch(self, frames, b):
-        return self._batch_host(lib().b200timg_sixel_batch, frames, b)
+        return self._batch_host(lib().b200timg_sixel_batch, frames, b, sixel=True)

@@ -235,9 +235,10 @@ int b200timg_scale_rgba(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, in
 
 // ---- sixel -----------------------------------------------------------------------------
 size_t b200timg_sixel_bound(int w, int h) {
-    // header + 256 palette definitions + per band: per colour "#ddd" + w sixels + "$" ; "-"
+    // our stream: header + <=256 palette definitions; per 6-row band every column has <= 6
+    // (colour, bits) entries of <= 7 bytes amortised ("!nnnn?" gap + char), plus "$#ccc" per colour
     const size_t bands = (size_t)(h + 5) / 6;
-    return 64 + 256 * 20 + bands * (256 * (size_t)(5 + 1) + (size_t)w * 6 + 2) + 8;
+    return 32 + 256 * 18 + bands * ((size_t)w * 42 + 256 * 5 + 1) + 2;
 }
 
 int b200timg_sixel_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, char *out, size_t cap,
@@ -246,21 +247,26 @@ int b200timg_sixel_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, ch
     if (!fb || !size || w <= 0 || h <= 0 || (h % 6) != 0 || (!out && cap))
         return ctx->fail(B200TIMG_EINVAL, "sixel: bad args (height must be a multiple of 6)");
     const size_t bytes = (size_t)w * h * 4;
-    const size_t bound = b200timg_sixel_bound(w, h);
     B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
-    B2_CUDA(ctx, ctx->out_stage.reserve(bound));
     B2_CUDA(ctx, ctx->offsets.reserve(2 * sizeof(uint64_t)));
     B2_CUDA(ctx, ctx->pinned.reserve(64));
     B2_TRY(upload(ctx, ctx->fb_scaled.p, fb, bytes));
-    B2_TRY(launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, ctx->out_stage.as<char>(), bound,
-                        ctx->offsets.as<uint64_t>()));
+    B2_TRY(launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, nullptr, 0, ctx->offsets.as<uint64_t>(), 1));
     B2_TRY(download(ctx, ctx->pinned.p, ctx->offsets.p, 2 * sizeof(uint64_t)));
     B2_TRY(sync(ctx));
     const size_t n = (size_t)ctx->pinned.as<uint64_t>()[1];
     *size = n;
     if (n > cap) return ctx->fail(B200TIMG_ENOSPC, "sixel: need %zu bytes, have %zu", n, cap);
+    B2_CUDA(ctx, ctx->out_stage.reserve(n));
+    B2_TRY(launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, ctx->out_stage.as<char>(), n,
+                        ctx->offsets.as<uint64_t>(), 2));
     B2_TRY(download(ctx, out, ctx->out_stage.p, n));
     return sync(ctx);
+}
+
+int b200timg_sixel_debug(b200timg_ctx *ctx, uint32_t *palette, uint32_t *counts, uint8_t *index, size_t index_bytes) {
+    B2_TRY(check_ctx(ctx));
+    return sixel_debug_fetch(ctx, palette, counts, index, index_bytes);
 }
 
 // ---- batches -----------------------------------------------------------------------------
@@ -285,11 +291,12 @@ int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const 
                          b->x_indent_cells, d_out, out_cap, d_offsets);
 }
 
-int b200timg_sixel_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,
-                             char *d_out, size_t out_cap, uint64_t *d_offsets) {
-    B2_TRY(check_ctx(ctx));
-    B2_TRY(validate_batch(ctx, b));
-    if (!d_src || !d_out || !d_offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
+static int sixel_batch_phases(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,
+                              char *d_out, size_t out_cap, uint64_t *d_offsets, int phases) {
+    if (phases == 2) {   // scaled frames are still in ctx->fb_scaled from the prepare phase
+        return launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), b->out_w, round_to_sixel(b->out_h), b->n_frames, d_out,
+                            out_cap, d_offsets, 2);
+    }
     // SixelCanvas::Send (src/sixel-canvas.cc:109-120): pad to a multiple of 6 rows with
     // transparent pixels, compose the background into the pad strip only, keep the rest.
     const int hp = round_to_sixel(b->out_h);
@@ -303,7 +310,15 @@ int b200timg_sixel_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const u
     //  which is exactly what the canvas' own start_row=h call (:115-118) produces.)
     B2_TRY(launch_compose(ctx, d_fb, b->out_w, hp, b->n_frames, b->has_bg, b->bg, b->pattern, b->pattern_w,
                           b->pattern_h, 0));
-    return launch_sixel(ctx, d_fb, b->out_w, hp, b->n_frames, d_out, out_cap, d_offsets);
+    return launch_sixel(ctx, d_fb, b->out_w, hp, b->n_frames, d_out, out_cap, d_offsets, phases);
+}
+
+int b200timg_sixel_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,
+                             char *d_out, size_t out_cap, uint64_t *d_offsets) {
+    B2_TRY(check_ctx(ctx));
+    B2_TRY(validate_batch(ctx, b));
+    if (!d_src || !d_out || !d_offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
+    return sixel_batch_phases(ctx, b, d_src, d_out, out_cap, d_offsets, 3);
 }
 
 static int batch_host(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,
@@ -312,19 +327,27 @@ static int batch_host(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t 
     B2_TRY(validate_batch(ctx, b));
     if (!src || !out || !offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
     const size_t in_bytes = (size_t)b->src_w * b->src_h * 4 * b->n_frames;
-    const size_t per = sixel ? b200timg_sixel_bound(b->out_w, round_to_sixel(b->out_h))
-                             : b200timg_blocks_bound(b->out_w, b->out_h);
-    const size_t bound = per * b->n_frames + 64;
+    const size_t off_bytes = (size_t)(b->n_frames + 1) * sizeof(uint64_t);
     B2_CUDA(ctx, ctx->in_stage.reserve(in_bytes));
-    B2_CUDA(ctx, ctx->out_stage.reserve(bound));
-    B2_CUDA(ctx, ctx->offsets.reserve((size_t)(b->n_frames + 1) * sizeof(uint64_t)));
+    B2_CUDA(ctx, ctx->offsets.reserve(off_bytes));
     B2_TRY(upload(ctx, ctx->in_stage.p, src, in_bytes));
-    int rc = sixel ? b200timg_sixel_batch_dev(ctx, b, ctx->in_stage.as<uint8_t>(), ctx->out_stage.as<char>(), bound,
-                                              ctx->offsets.as<uint64_t>())
-                   : b200timg_blocks_batch_dev(ctx, b, ctx->in_stage.as<uint8_t>(), ctx->out_stage.as<char>(), bound,
-                                               ctx->offsets.as<uint64_t>());
-    if (rc != B200TIMG_OK) return rc;
-    B2_TRY(download(ctx, offsets, ctx->offsets.p, (size_t)(b->n_frames + 1) * sizeof(uint64_t)));
+    if (sixel) {
+        // sizes first (exact), then bytes: the encoded stream is sized before it is written
+        B2_TRY(sixel_batch_phases(ctx, b, ctx->in_stage.as<uint8_t>(), nullptr, 0, ctx->offsets.as<uint64_t>(), 1));
+        B2_TRY(download(ctx, offsets, ctx->offsets.p, off_bytes));
+        B2_TRY(sync(ctx));
+        const size_t total = (size_t)offsets[b->n_frames];
+        if (total > out_cap) return ctx->fail(B200TIMG_ENOSPC, "batch: need %zu bytes, have %zu", total, out_cap);
+        B2_CUDA(ctx, ctx->out_stage.reserve(total));
+        B2_TRY(sixel_batch_phases(ctx, b, nullptr, ctx->out_stage.as<char>(), total, ctx->offsets.as<uint64_t>(), 2));
+        B2_TRY(download(ctx, out, ctx->out_stage.p, total));
+        return sync(ctx);
+    }
+    const size_t bound = b200timg_blocks_bound(b->out_w, b->out_h) * b->n_frames + 64;
+    B2_CUDA(ctx, ctx->out_stage.reserve(bound));
+    B2_TRY(b200timg_blocks_batch_dev(ctx, b, ctx->in_stage.as<uint8_t>(), ctx->out_stage.as<char>(), bound,
+                                     ctx->offsets.as<uint64_t>()));
+    B2_TRY(download(ctx, offsets, ctx->offsets.p, off_bytes));
     B2_TRY(sync(ctx));
     const size_t total = (size_t)offsets[b->n_frames];
     if (total > out_cap) return ctx->fail(B200TIMG_ENOSPC, "batch: need %zu bytes, have %zu", total, out_cap);

@@ -55,6 +55,7 @@ struct b200timg_ctx {
     int device = 0;
     b200timg::ResamplePlan *plan = nullptr;   // cached resampling tables (host copy) ...
     int plan_key[4] = {0, 0, 0, 0};           // ... for this iw, ih, ow, oh (device copy in `tables`)
+    size_t sixel_idx_off = 0;                 // where the last sixel encode put its index planes
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
@@ -145,6 +146,7 @@ int launch_blocks(b200timg_ctx *ctx, const uint8_t *d_fb, const uint8_t *d_prev,
 int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out,
                  int ow, int oh, int out_frame_rows, int n_frames);
 int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
-                 size_t out_cap, uint64_t *d_offsets);
+                 size_t out_cap, uint64_t *d_offsets, int phases);
+int sixel_debug_fetch(b200timg_ctx *ctx, uint32_t *h_palette, uint32_t *h_counts, uint8_t *h_index, size_t index_bytes);
 
 }  // namespace b200timg

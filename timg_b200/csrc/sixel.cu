@@ -1,0 +1,709 @@
+// K4-K6: what libsixel computes inside SixelCanvas::Send (src/sixel-canvas.cc:134-148) --
+//   sixel_dither_new(256); sixel_dither_initialize(RGBA8888, LARGE_LUM, REP_AVERAGE_COLORS,
+//   QUALITY_AUTO); sixel_encode(...)
+// restated for the device.  libsixel is not part of the reference tree; the algorithm below is
+// the published one (quant.c: computeHistogram / mediancut / lookup_fast / diffuse_fs; tosixel.c)
+// with the two raster-order dependencies replaced by order-free rules so it can run in parallel
+// (oracle/sixel_oracle.c "mode 1" is the CPU statement of exactly these semantics, and the tests
+// require bit-identical palettes / index planes / decoded images against it):
+//   * the colour table handed to median cut starts in bucket order (libsixel: first-seen order;
+//     only the treatment of equal sort keys differs);
+//   * the nearest-palette memo of a 15-bit colour cell is the nearest entry to the cell CENTRE
+//     (libsixel: to the first pixel that happened to hit the cell in raster order).
+// Everything else -- sampling stride, 15-bit histogram, luminance-weighted split axis, median by
+// pixel count, box order by population, plain-mean representative, Floyd-Steinberg with the error
+// added into 8-bit clamped pixels tap by tap (7/16 right, 3/16 below-left, 5/16 below, 1/16
+// below-right, C truncation, no diffusion from the last row/column, x=0's below-left tap landing
+// on the same row's last pixel) -- is libsixel's.
+//
+// Kernels (per frame unless noted):
+//   sixel_palette_kernel   1 CTA : sampled histogram (packed u16 smem atomics) -> compaction ->
+//                                  median cut (stable counting sort by 5-bit key, block scans)
+//   sixel_lut_kernel       32 CTAs: 32768-entry nearest-colour table
+//   sixel_dither_kernel    1 CTA : FS wavefront; a warp owns a band of 32 rows with a 2-column
+//                                  skew between lanes (errors handed down by shuffle), bands are
+//                                  pipelined warp to warp through a boundary row + progress flag
+//   sixel_emit_kernel<0/1> 1 CTA per 6-row band: sizes, then bytes (per-colour RLE rows)
+// Algorithmic bytes per frame: 4*W*H read + encoded bytes written; index plane (1 B/px), boundary
+// rows, LUT and tables are intermediates.
+#include "common.cuh"
+
+namespace b200timg {
+
+struct SixelFrameHdr {
+    uint32_t ncolors, origcolors, diffuse, header_len;
+    uint32_t frame_size, pad0, pad1, pad2;
+    uint32_t palette[256];             // r | g << 8 | b << 16
+};
+
+struct SixelWork {                     // device pointers into ctx->sixel_work
+    SixelFrameHdr *hdr;                // [n_frames]
+    uint32_t *ent_a, *ent_b;           // [n_frames][ent_cap] median-cut tables (bucket << 16 | count)
+    uint8_t *lut;                      // [n_frames][32768]
+    uint8_t *index;                    // [n_frames][w*h]
+    uint32_t *boundary;                // [n_frames][nb32][w] packed errors of each 32-row band's last row
+    uint32_t *band_bytes;              // [n_frames][nbands]  (sizes, then exclusive offsets in place)
+    int ent_cap, nb32, nbands;
+};
+
+__device__ __forceinline__ uint32_t hash15(uint32_t px) {   // (r>>3)<<10 | (g>>3)<<5 | (b>>3)
+    return ((px & 0xf8) << 7) | ((px >> 6) & 0x3e0) | ((px >> 19) & 0x1f);
+}
+__device__ __forceinline__ uint32_t key5(uint32_t entry, int plane) { return (entry >> (26 - 5 * plane)) & 31; }
+
+// ------------------------------------------------------------------ block helpers (1024 thr)
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*[NT/32]*/, uint32_t &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+    for (int k = 0; k < NT / 32; ++k) { if (k < wid) pre += s_w[k]; tot += s_w[k]; }
+    total = tot;
+    __syncthreads();
+    return pre + inc - v;
+}
+
+constexpr int PT = 1024;   // palette kernel threads
+
+__global__ void __launch_bounds__(PT)
+sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W) {
+    extern __shared__ uint32_t s_hist[];               // 16384 words: two u16 counters per word
+    __shared__ uint32_t s_w[PT / 32];
+    __shared__ int b_ind[256], b_col[256], t_ind[256], t_col[256];
+    __shared__ uint32_t b_sum[256], t_sum[256];
+    __shared__ int s_mn[3], s_mx[3];
+    __shared__ uint32_t s_cnt[32], s_base[32], s_run[32];
+    __shared__ unsigned short s_wh[32][32];
+    __shared__ int s_bi, s_plane, s_boxes;
+    __shared__ unsigned long long s_med;
+
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long npix = (long long)w * h;
+    const uint32_t *frame = fb + (long long)f * npix;
+    SixelFrameHdr *hdr = W.hdr + f;
+    uint32_t *E = W.ent_a + (long long)f * W.ent_cap, *T = W.ent_b + (long long)f * W.ent_cap;
+
+    // quant.c computeHistogram, QUALITY_LOW: step = length/depth/max_sample*depth (bytes)
+    unsigned long long step_px = (unsigned long long)npix / 18383ull;
+    if ((unsigned long long)npix < 18383ull) step_px = 6;
+    if (step_px == 0) step_px = 1;
+    const long long ns = (npix + (long long)step_px - 1) / (long long)step_px;
+
+    for (int i = tid; i < 16384; i += PT) s_hist[i] = 0;
+    __syncthreads();
+    for (long long k = tid; k < ns; k += PT) {
+        const uint32_t b = hash15(frame[k * (long long)step_px]);
+        atomicAdd(&s_hist[b >> 1], 1u << (16 * (b & 1)));    // counts <= ns <= 36766 < 65536: no carry
+    }
+    __syncthreads();
+    // compaction in bucket order: thread t owns buckets [32t, 32t+32)
+    uint32_t mine = 0;
+    for (int k = 0; k < 16; ++k) { const uint32_t v = s_hist[tid * 16 + k]; mine += ((v & 0xffff) != 0) + ((v >> 16) != 0); }
+    uint32_t n_ent;
+    uint32_t pos = block_excl_scan<PT>(mine, s_w, n_ent);
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t v = s_hist[tid * 16 + k];
+        const uint32_t b0 = (uint32_t)(tid * 32 + 2 * k);
+        if (v & 0xffff) E[pos++] = (b0 << 16) | (v & 0xffff);
+        if (v >> 16) E[pos++] = ((b0 + 1) << 16) | (v >> 16);
+    }
+    __syncthreads();
+    if (tid == 0) { hdr->origcolors = n_ent; hdr->diffuse = n_ent > 256 ? 1 : 0; }
+    if (n_ent <= 256) {                                 // "Image already has few enough colors"
+        if (tid < 256) {
+            uint32_t pal = 0;
+            if ((uint32_t)tid < n_ent) { const uint32_t e = E[tid]; pal = (key5(e, 0) << 3) | (key5(e, 1) << 11) | (key5(e, 2) << 19); }
+            hdr->palette[tid] = pal;
+        }
+        if (tid == 0) hdr->ncolors = n_ent;
+        return;
+    }
+    // ---- mediancut()
+    {
+        uint32_t s = 0;
+        for (uint32_t i = tid; i < n_ent; i += PT) s += E[i] & 0xffff;
+        uint32_t total; const uint32_t dummy = block_excl_scan<PT>(s, s_w, total); (void)dummy;
+        if (tid == 0) { b_ind[0] = 0; b_col[0] = (int)n_ent; b_sum[0] = total; s_boxes = 1; }
+    }
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) {
+            int bi = 0; const int nb = s_boxes;
+            while (bi < nb && b_col[bi] < 2) ++bi;
+            s_bi = (nb < 256 && bi < nb) ? bi : -1;
+            s_mn[0] = s_mn[1] = s_mn[2] = 31; s_mx[0] = s_mx[1] = s_mx[2] = 0;
+            s_med = ~0ull;
+        }
+        if (tid < 32) { s_cnt[tid] = 0; s_run[tid] = 0; }
+        __syncthreads();
+        const int bi = s_bi;
+        if (bi < 0) break;
+        const int start = b_ind[bi], size = b_col[bi];
+        const uint32_t sm = b_sum[bi];
+        uint32_t *B = E + start, *TB = T + start;
+        // findBoxBoundaries
+        int mn0 = 31, mn1 = 31, mn2 = 31, mx0 = 0, mx1 = 0, mx2 = 0;
+        for (int i = tid; i < size; i += PT) {
+            const uint32_t e = B[i];
+            const int k0 = key5(e, 0), k1 = key5(e, 1), k2 = key5(e, 2);
+            mn0 = min(mn0, k0); mx0 = max(mx0, k0); mn1 = min(mn1, k1); mx1 = max(mx1, k1); mn2 = min(mn2, k2); mx2 = max(mx2, k2);
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, d)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
+            mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+            mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, d)); mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, d));
+        }
+        if (lane == 0) {
+            atomicMin(&s_mn[0], mn0); atomicMax(&s_mx[0], mx0); atomicMin(&s_mn[1], mn1); atomicMax(&s_mx[1], mx1);
+            atomicMin(&s_mn[2], mn2); atomicMax(&s_mx[2], mx2);
+        }
+        __syncthreads();
+        if (tid == 0) {                                  // largestByLuminosity (colour values are key << 3)
+            const double lum[3] = {0.2989, 0.5866, 0.1145};
+            int plane = 0; double best = 0.0;
+            for (int p = 0; p < 3; ++p) {
+                const double spread = lum[p] * (double)((s_mx[p] - s_mn[p]) << 3);
+                if (spread > best) { plane = p; best = spread; }
+            }
+            s_plane = plane;
+        }
+        __syncthreads();
+        const int plane = s_plane;
+        // stable counting sort of the box by the 5-bit key of `plane` (qsort + compareplane)
+        for (int i = tid; i < size; i += PT) atomicAdd(&s_cnt[key5(B[i], plane)], 1u);
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t c = s_cnt[tid]; uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+            s_base[tid] = inc - c;
+        }
+        for (int t0 = 0; t0 < size; t0 += PT) {
+            s_wh[wid][lane] = 0;
+            __syncthreads();
+            const int i = t0 + tid;
+            const bool valid = i < size;
+            uint32_t e = 0, k = 0, rank = 0;
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                e = B[i]; k = key5(e, plane);
+                const uint32_t m = __match_any_sync(vmask, k);
+                rank = __popc(m & ((1u << lane) - 1));
+                if (rank == 0) s_wh[wid][k] = (unsigned short)__popc(m);
+            }
+            __syncthreads();
+            if (valid) {
+                uint32_t p = s_base[k] + s_run[k] + rank;
+                for (int w2 = 0; w2 < wid; ++w2) p += s_wh[w2][k];
+                TB[p] = e;
+            }
+            __syncthreads();
+            if (tid < 32) { uint32_t a = 0; for (int w2 = 0; w2 < 32; ++w2) a += s_wh[w2][tid]; s_run[tid] += a; }
+            __syncthreads();
+        }
+        for (int i = tid; i < size; i += PT) B[i] = TB[i];
+        __syncthreads();
+        // median by pixel count: smallest i in [1, size-2] with sum(count[0..i)) >= sm/2, else size-1
+        {
+            const uint32_t half = sm / 2;
+            uint32_t carry = 0;
+            for (int t0 = 0; t0 < size; t0 += PT) {
+                const int i = t0 + tid;
+                const uint32_t c = i < size ? (B[i] & 0xffff) : 0;
+                uint32_t tot; const uint32_t before = carry + block_excl_scan<PT>(c, s_w, tot);
+                if (i >= 1 && i <= size - 2 && before >= half) atomicMin(&s_med, ((unsigned long long)i << 32) | before);
+                carry += tot;
+                __syncthreads();                         // make the atomicMin visible, keep the exit uniform
+                if (s_med != ~0ull) break;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int median; uint32_t lower;
+            if (s_med != ~0ull) { median = (int)(s_med >> 32); lower = (uint32_t)s_med; }
+            else { median = size - 1; lower = sm - (B[size - 1] & 0xffff); }
+            const int nb = s_boxes;
+            b_col[bi] = median; b_sum[bi] = lower;
+            b_ind[nb] = start + median; b_col[nb] = size - median; b_sum[nb] = sm - lower;
+            s_boxes = nb + 1;
+        }
+        __syncthreads();
+        {                                               // qsort(bv, boxes, sumcompare): stable, descending
+            const int nb = s_boxes;
+            if (tid < nb) {
+                const uint32_t me = b_sum[tid]; int r = 0;
+                for (int j = 0; j < nb; ++j) { const uint32_t o = b_sum[j]; r += (o > me) || (o == me && j < tid); }
+                t_ind[r] = b_ind[tid]; t_col[r] = b_col[tid]; t_sum[r] = me;
+            }
+            __syncthreads();
+            if (tid < nb) { b_ind[tid] = t_ind[tid]; b_col[tid] = t_col[tid]; b_sum[tid] = t_sum[tid]; }
+            __syncthreads();
+        }
+    }
+    // colormapFromBv, SIXEL_REP_AVERAGE_COLORS: plain mean of the box's colour values
+    if (tid < 256) {
+        uint32_t pal = 0;
+        if (tid < s_boxes) {
+            uint32_t s0 = 0, s1 = 0, s2 = 0; const int st = b_ind[tid], n = b_col[tid];
+            for (int i = 0; i < n; ++i) { const uint32_t e = E[st + i]; s0 += key5(e, 0) << 3; s1 += key5(e, 1) << 3; s2 += key5(e, 2) << 3; }
+            pal = (s0 / (uint32_t)n) | ((s1 / (uint32_t)n) << 8) | ((s2 / (uint32_t)n) << 16);
+        }
+        hdr->palette[tid] = pal;
+    }
+    if (tid == 0) hdr->ncolors = 256;
+}
+
+// nearest palette entry (first minimum, complexion 1) for the centre of every 15-bit cell
+__global__ void __launch_bounds__(256)
+sixel_lut_kernel(SixelWork W) {
+    __shared__ uint32_t s_pal[256];
+    const int f = blockIdx.y;
+    const SixelFrameHdr *hdr = W.hdr + f;
+    s_pal[threadIdx.x] = hdr->palette[threadIdx.x];
+    __syncthreads();
+    const int n = (int)hdr->ncolors;
+    const uint32_t cell = blockIdx.x * 256 + threadIdx.x;
+    const int r = (int)(((cell >> 10) & 31) << 3 | 4), g = (int)(((cell >> 5) & 31) << 3 | 4), b = (int)((cell & 31) << 3 | 4);
+    int best = 0x7fffffff, bi = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t p = s_pal[i];
+        const int dr = r - (int)(p & 0xff), dg = g - (int)((p >> 8) & 0xff), db = b - (int)((p >> 16) & 0xff);
+        const int d = dr * dr + dg * dg + db * db;
+        if (d < best) { best = d; bi = i; }
+    }
+    W.lut[(long long)f * 32768 + cell] = (uint8_t)bi;
+}
+
+// no diffusion (<= 256 distinct sampled colours): plain table lookup per pixel
+__global__ void __launch_bounds__(256)
+sixel_map_kernel(const uint32_t *__restrict__ fb, long long npix, SixelWork W) {
+    const int f = blockIdx.y;
+    if (W.hdr[f].diffuse) return;
+    const uint8_t *lut = W.lut + (long long)f * 32768;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride)
+        W.index[(long long)f * npix + i] = lut[hash15(fb[(long long)f * npix + i])];
+}
+
+// ---- Floyd-Steinberg wavefront --------------------------------------------------------------
+constexpr uint32_t EZ = 256u | (256u << 9) | (256u << 18);     // packed zero error (each channel biased by 256)
+__device__ __forceinline__ int fs_tap(int v, int e, int k) {      // error_diffuse(): c = v + e*k/16, clamp
+    const int t = e * k;
+    const int q = (t + ((t >> 31) & 15)) >> 4;                  // C division truncates toward zero
+    return min(255, max(0, v + q));
+}
+constexpr int DW = 16;                                            // warps per frame CTA
+
+__global__ void __launch_bounds__(DW * 32)
+sixel_dither_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W) {
+    extern __shared__ uint8_t s_lut[];                            // 32768
+    __shared__ uint32_t s_pal[256];
+    __shared__ volatile int s_progress[2048];                     // columns completed by each band's last row
+    const int f = blockIdx.x;
+    const SixelFrameHdr *hdr = W.hdr + f;
+    if (!hdr->diffuse) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < 32768 / 4; i += DW * 32)
+        reinterpret_cast<uint32_t *>(s_lut)[i] = reinterpret_cast<const uint32_t *>(W.lut + (long long)f * 32768)[i];
+    if (tid < 256) s_pal[tid] = hdr->palette[tid];
+    for (int i = tid; i < W.nb32; i += DW * 32) s_progress[i] = 0;
+    __syncthreads();
+    const uint32_t *frame = fb + (long long)f * w * h;
+    uint8_t *index = W.index + (long long)f * w * h;
+    uint32_t *bnd = W.boundary + (long long)f * W.nb32 * w;
+
+    for (int band = wid; band < W.nb32; band += DW) {
+        const int y = band * 32 + lane;
+        const bool row_ok = y < h;
+        const uint32_t *rowp = frame + (long long)(row_ok ? y : 0) * w;
+        uint8_t *outp = index + (long long)(row_ok ? y : 0) * w;
+        const uint32_t *bin = band > 0 ? bnd + (long long)(band - 1) * w : nullptr;
+        uint32_t *bout = bnd + (long long)band * w;
+        const bool last_row = (y == h - 1);
+        uint32_t last_e = EZ, up_m1 = EZ, up_0 = EZ, up_p1 = EZ, own = EZ, e_first = EZ;
+        const int steps = w + 62;
+        for (int t = 0; t < steps; ++t) {
+            if (band > 0 && (t & 31) == 0) {                      // stay behind the previous band's last row
+                const int need = min(w, t + 33);
+                if (lane == 0) while (s_progress[band - 1] < need) __nanosleep(64);
+                __syncwarp();
+            }
+            const int x = t - 2 * lane;
+            uint32_t recv = __shfl_up_sync(0xffffffffu, last_e, 1);
+            if (lane == 0) recv = (bin && x + 1 < w) ? __ldcg(bin + x + 1) : EZ;
+            up_m1 = up_0; up_0 = up_p1; up_p1 = recv;
+            if (x >= 0 && x < w && row_ok) {
+                const uint32_t px = rowp[x];
+                int v[3] = {(int)(px & 0xff), (int)((px >> 8) & 0xff), (int)((px >> 16) & 0xff)};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int sh = 9 * c;
+                    v[c] = fs_tap(v[c], (int)((up_m1 >> sh) & 511) - 256, 1);      // from (x-1, y-1)
+                    v[c] = fs_tap(v[c], (int)((up_0 >> sh) & 511) - 256, 5);       // from (x,   y-1)
+                    v[c] = fs_tap(v[c], (int)((up_p1 >> sh) & 511) - 256, 3);      // from (x+1, y-1)
+                    if (x == w - 1) v[c] = fs_tap(v[c], (int)((e_first >> sh) & 511) - 256, 3);   // libsixel: (0,y)'s below-left tap
+                    v[c] = fs_tap(v[c], (int)((own >> sh) & 511) - 256, 7);        // from (x-1, y)
+                }
+                const uint32_t cell = ((uint32_t)(v[0] >> 3) << 10) | ((uint32_t)(v[1] >> 3) << 5) | (uint32_t)(v[2] >> 3);
+                const uint32_t ci = s_lut[cell];
+                const uint32_t pal = s_pal[ci];
+                uint32_t e = EZ;
+                if (x < w - 1 && !last_row)
+                    e = (uint32_t)(v[0] - (int)(pal & 0xff) + 256) | ((uint32_t)(v[1] - (int)((pal >> 8) & 0xff) + 256) << 9)
+                      | ((uint32_t)(v[2] - (int)((pal >> 16) & 0xff) + 256) << 18);
+                if (x == 0) e_first = e;
+                own = e; last_e = e;
+                outp[x] = (uint8_t)ci;
+                if (lane == 31) {
+                    __stcg(bout + x, e);
+                    if ((x & 31) == 31 || x == w - 1) { __threadfence_block(); s_progress[band] = x + 1; }
+                }
+            } else if (x >= w) {
+                last_e = EZ;
+            }
+        }
+        if (lane == 31 && !row_ok) { __threadfence_block(); s_progress[band] = w; }   // ragged last band: nobody waits, but be tidy
+    }
+}
+
+// ---- emit ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ndig_u(uint32_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
+__device__ __forceinline__ uint32_t rle_len(uint32_t n) { return n == 0 ? 0 : (n > 3 ? 2 + ndig_u(n) : n); }   // tosixel.c sixel_put_flash
+__device__ __forceinline__ char *put_num_u(char *o, uint32_t v) {
+    char tmp[10]; int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *o++ = tmp[--n];
+    return o;
+}
+__device__ __forceinline__ char *put_rle(char *o, uint32_t n, char ch) {
+    if (n > 3) { *o++ = '!'; o = put_num_u(o, n); *o++ = ch; }
+    else for (uint32_t i = 0; i < n; ++i) *o++ = ch;
+    return o;
+}
+
+constexpr int ET = 512;
+constexpr uint32_t ENT_INVALID = 0xffffffffu;
+// ent word: colour [0:8) | bits [8:14) | bytes [16:24)
+
+struct EmitGeom { int w, h, words, chunks, group; };   // words = ceil(w/32), chunks = ceil(w/64), group = colours per pass
+
+__device__ __forceinline__ uint32_t bits_of(const uint32_t *ent, int w, int x, uint32_t c) {
+#pragma unroll
+    for (int s = 0; s < 6; ++s) { const uint32_t e = ent[s * w + x]; if (e != ENT_INVALID && (e & 0xff) == c) return (e >> 8) & 63; }
+    return 0;
+}
+__device__ __forceinline__ uint32_t bytes_of(const uint32_t *ent, int w, int x, uint32_t c) {
+#pragma unroll
+    for (int s = 0; s < 6; ++s) { const uint32_t e = ent[s * w + x]; if (e != ENT_INVALID && (e & 0xff) == c) return (e >> 16) & 0xff; }
+    return 0;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(ET)
+sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets, char *__restrict__ out,
+                  unsigned long long out_cap) {
+    extern __shared__ uint32_t s_mem[];
+    uint32_t *ent = s_mem;                                   // [6][w]
+    uint32_t *P = ent + 6 * G.w;                             // [group][words]
+    uint32_t *S = P + G.group * G.words;                     // [group][chunks]
+    __shared__ uint32_t s_w[ET / 32];
+    __shared__ uint32_t s_minc, s_run;
+    const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int w = G.w;
+    const SixelFrameHdr *hdr = W.hdr + f;
+    const uint8_t *idx = W.index + ((long long)f * G.h + (long long)band * 6) * w;
+
+    unsigned long long fbase = 0; uint32_t band_off = 0;
+    if (WRITE) {
+        fbase = offsets[f];
+        if (fbase + hdr->frame_size > out_cap) return;       // never write out of bounds
+        band_off = W.band_bytes[(long long)f * W.nbands + band];
+    }
+    if (tid == 0) { s_minc = 256; s_run = 0; }
+    __syncthreads();
+    // distinct (colour, bits) pairs of every column of this 6-row band
+    uint32_t my_min = 256;
+    for (int x = tid; x < w; x += ET) {
+        uint32_t c[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c[i] = idx[(long long)i * w + x];
+        int ns = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            bool seen = false;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) if (j < i && c[j] == c[i]) seen = true;
+            if (!seen) {
+                uint32_t bits = 0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) if (j >= i && c[j] == c[i]) bits |= 1u << j;
+                ent[ns * w + x] = c[i] | (bits << 8);
+                my_min = min(my_min, c[i]);
+                ++ns;
+            }
+        }
+        for (; ns < 6; ++ns) ent[ns * w + x] = ENT_INVALID;
+    }
+    atomicMin(&s_minc, my_min);
+    __syncthreads();
+    const uint32_t minc = s_minc;
+
+    if (WRITE && band == 0) {                                // header: DCS q, raster attributes, palette
+        char *o = out + fbase;
+        if (tid == 0) {
+            *o++ = '\033'; *o++ = 'P'; *o++ = 'q'; *o++ = '"'; *o++ = '1'; *o++ = ';'; *o++ = '1'; *o++ = ';';
+            o = put_num_u(o, (uint32_t)w); *o++ = ';'; o = put_num_u(o, (uint32_t)G.h);
+        }
+        const uint32_t fixed = 8 + ndig_u((uint32_t)w) + 1 + ndig_u((uint32_t)G.h);
+        uint32_t len = 0, r = 0, g = 0, b = 0;
+        if ((uint32_t)tid < hdr->ncolors) {                  // output_rgb_palette_definition: (v*100+127)/255 percent
+            const uint32_t p = hdr->palette[tid];
+            r = ((p & 0xff) * 100 + 127) / 255; g = (((p >> 8) & 0xff) * 100 + 127) / 255; b = (((p >> 16) & 0xff) * 100 + 127) / 255;
+            len = 1 + ndig_u((uint32_t)tid) + 3 + ndig_u(r) + 1 + ndig_u(g) + 1 + ndig_u(b);
+        }
+        uint32_t tot; const uint32_t at = block_excl_scan<ET>(len, s_w, tot);
+        if (len) {
+            char *q = out + fbase + fixed + at;
+            *q++ = '#'; q = put_num_u(q, (uint32_t)tid); *q++ = ';'; *q++ = '2'; *q++ = ';';
+            q = put_num_u(q, r); *q++ = ';'; q = put_num_u(q, g); *q++ = ';'; q = put_num_u(q, b);
+        }
+    }
+    if (WRITE && tid == 0) {
+        if (band > 0) out[fbase + band_off - 1] = '-';       // DECGNL between bands
+        if (band == W.nbands - 1) { out[fbase + hdr->frame_size - 2] = '\033'; out[fbase + hdr->frame_size - 1] = '\\'; }
+    }
+
+    for (int g0 = 0; g0 < 256; g0 += G.group) {
+        for (int i = tid; i < G.group * (G.words + G.chunks); i += ET) P[i] = 0;   // P and S are contiguous
+        __syncthreads();
+        for (int x = tid; x < w; x += ET)
+#pragma unroll
+            for (int s = 0; s < 6; ++s) {
+                const uint32_t e = ent[s * w + x];
+                if (e == ENT_INVALID) break;
+                const int c = (int)(e & 0xff) - g0;
+                if (c >= 0 && c < G.group) atomicOr(&P[c * G.words + (x >> 5)], 1u << (x & 31));
+            }
+        __syncthreads();
+        for (int x = tid; x < w; x += ET)
+#pragma unroll
+            for (int s = 0; s < 6; ++s) {
+                const uint32_t e = ent[s * w + x];
+                if (e == ENT_INVALID) break;
+                const uint32_t c = e & 0xff;
+                const int cg = (int)c - g0;
+                if (cg < 0 || cg >= G.group) continue;
+                const uint32_t bits = (e >> 8) & 63;
+                const uint32_t *Pc = P + cg * G.words;
+                int j = x >> 5;
+                uint32_t m = Pc[j] & ((1u << (x & 31)) - 1);
+                while (m == 0 && --j >= 0) m = Pc[j];
+                const int px = m ? j * 32 + 31 - __clz(m) : -1;
+                uint32_t bytes = 0;
+                if (!(px == x - 1 && bits_of(ent, w, px, c) == bits)) {        // head of a run
+                    uint32_t L = 1; int nx = x + 1;
+                    while (nx < w && ((Pc[nx >> 5] >> (nx & 31)) & 1) && bits_of(ent, w, nx, c) == bits) { ++L; ++nx; }
+                    bytes = rle_len((uint32_t)(x - px - 1)) + rle_len(L);
+                    if (px < 0) bytes += 1 + ndig_u(c) + (c != minc ? 1 : 0);   // "#c", preceded by '$' unless first row
+                    atomicAdd(&S[cg * G.chunks + (x >> 6)], bytes);
+                }
+                ent[s * w + x] = (e & 0xffff) | (bytes << 16);
+            }
+        __syncthreads();
+        // exclusive scan of S in colour-major order (each thread owns a contiguous slice)
+        const int nS = G.group * G.chunks, per = (nS + ET - 1) / ET;
+        const int lo = tid * per, hi = min(nS, lo + per);
+        uint32_t local = 0;
+        for (int i = lo; i < hi; ++i) local += S[i];
+        uint32_t gtot; uint32_t at = block_excl_scan<ET>(local, s_w, gtot);
+        for (int i = lo; i < hi; ++i) { const uint32_t v = S[i]; S[i] = at; at += v; }
+        __syncthreads();
+        if (WRITE) {
+            const uint32_t run = s_run;
+            for (int x = tid; x < w; x += ET)
+#pragma unroll
+                for (int s = 0; s < 6; ++s) {
+                    const uint32_t e = ent[s * w + x];
+                    if (e == ENT_INVALID) break;
+                    const uint32_t c = e & 0xff, bytes = (e >> 16) & 0xff;
+                    const int cg = (int)c - g0;
+                    if (cg < 0 || cg >= G.group || bytes == 0) continue;
+                    const uint32_t bits = (e >> 8) & 63;
+                    const uint32_t *Pc = P + cg * G.words;
+                    uint32_t off = run + S[cg * G.chunks + (x >> 6)];
+                    int px = -1;
+                    {   // earlier entries of this colour inside the same 64-column chunk
+                        const int j0 = (x >> 6) * 2, jx = x >> 5;
+                        for (int j = j0; j <= jx; ++j) {
+                            uint32_t m = Pc[j];
+                            if (j == jx) m &= (1u << (x & 31)) - 1;
+                            while (m) { const int b = __ffs(m) - 1; m &= m - 1; off += bytes_of(ent, w, j * 32 + b, c); }
+                        }
+                        int j = jx; uint32_t m = Pc[j] & ((1u << (x & 31)) - 1);
+                        while (m == 0 && --j >= 0) m = Pc[j];
+                        px = m ? j * 32 + 31 - __clz(m) : -1;
+                    }
+                    uint32_t L = 1; int nx = x + 1;
+                    while (nx < w && ((Pc[nx >> 5] >> (nx & 31)) & 1) && bits_of(ent, w, nx, c) == bits) { ++L; ++nx; }
+                    char *o = out + fbase + band_off + off;
+                    if (px < 0) { if (c != minc) *o++ = '$'; *o++ = '#'; o = put_num_u(o, c); }
+                    o = put_rle(o, (uint32_t)(x - px - 1), '?');
+                    o = put_rle(o, L, (char)('?' + bits));
+                }
+        }
+        __syncthreads();
+        if (tid == 0) s_run += gtot;
+        __syncthreads();
+    }
+    if (!WRITE && tid == 0) W.band_bytes[(long long)f * W.nbands + band] = s_run;
+}
+
+// per frame: header length, band offsets (exclusive, in place), frame size
+__global__ void __launch_bounds__(256)
+sixel_layout_kernel(int w, int h, SixelWork W) {
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_carry;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    SixelFrameHdr *hdr = W.hdr + f;
+    uint32_t len = 0;
+    if ((uint32_t)tid < hdr->ncolors) {
+        const uint32_t p = hdr->palette[tid];
+        const uint32_t r = ((p & 0xff) * 100 + 127) / 255, g = (((p >> 8) & 0xff) * 100 + 127) / 255, b = (((p >> 16) & 0xff) * 100 + 127) / 255;
+        len = 1 + ndig_u((uint32_t)tid) + 3 + ndig_u(r) + 1 + ndig_u(g) + 1 + ndig_u(b);
+    }
+    uint32_t pal_total; (void)block_excl_scan<256>(len, s_w, pal_total);
+    const uint32_t header = 8 + ndig_u((uint32_t)w) + 1 + ndig_u((uint32_t)h) + pal_total;
+    if (tid == 0) s_carry = header;
+    __syncthreads();
+    uint32_t *bb = W.band_bytes + (long long)f * W.nbands;
+    for (int b0 = 0; b0 < W.nbands; b0 += 256) {
+        const int b = b0 + tid;
+        const uint32_t v = b < W.nbands ? bb[b] + (b > 0 ? 1u : 0u) : 0;       // '-' before every band but the first
+        uint32_t tot; const uint32_t at = block_excl_scan<256>(v, s_w, tot);
+        if (b < W.nbands) bb[b] = s_carry + at + (b > 0 ? 1u : 0u);            // offset of the band's first data byte
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) { hdr->header_len = header; hdr->frame_size = s_carry + 2; }   // + ESC backslash
+}
+
+__global__ void __launch_bounds__(1024)
+sixel_sizes_to_offsets_kernel(const SixelFrameHdr *__restrict__ hdr, int n, uint64_t *__restrict__ offsets) {
+    __shared__ unsigned long long s_wv[32];
+    __shared__ unsigned long long c_run;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) c_run = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        unsigned long long v = i < n ? hdr[i].frame_size : 0ull;
+        const unsigned long long mine = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+        if (lane == 31) s_wv[wid] = v;
+        __syncthreads();
+        unsigned long long pre = 0, tot = 0;
+        for (int k = 0; k < 32; ++k) { if (k < wid) pre += s_wv[k]; tot += s_wv[k]; }
+        if (i < n) offsets[i] = c_run + pre + v - mine;
+        __syncthreads();
+        if (tid == 0) c_run += tot;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = c_run;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// phases: 1 = everything up to and including the frame offsets (sizes known, nothing written),
+//         2 = write the bytes.  3 = both, back to back without a host round trip.
+int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
+                 size_t out_cap, uint64_t *d_offsets, int phases) {
+    if (h % 6) return ctx->fail(B200TIMG_EINVAL, "sixel: height %d is not a multiple of 6", h);
+    if ((reinterpret_cast<uintptr_t>(d_fb) & 3)) return ctx->fail(B200TIMG_EINVAL, "sixel: framebuffer must be 4-byte aligned");
+    if (n_frames > 65535) return ctx->fail(B200TIMG_EINVAL, "sixel: too many frames for one launch");
+    const long long npix = (long long)w * h;
+    long long step_px = npix / 18383; if (npix < 18383) step_px = 6; if (step_px == 0) step_px = 1;
+    const long long ns = (npix + step_px - 1) / step_px;
+    SixelWork W;
+    W.ent_cap = (int)std::min<long long>(32768, ns);
+    W.nb32 = (h + 31) / 32; W.nbands = h / 6;
+    if (W.nb32 > 2048) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too tall");
+    // workspace carve-up
+    size_t off = 0;
+    const size_t o_hdr = off; off += align_up(sizeof(SixelFrameHdr) * n_frames, 256);
+    const size_t o_ea = off; off += align_up(sizeof(uint32_t) * (size_t)W.ent_cap * n_frames, 256);
+    const size_t o_eb = off; off += align_up(sizeof(uint32_t) * (size_t)W.ent_cap * n_frames, 256);
+    const size_t o_lut = off; off += align_up((size_t)32768 * n_frames, 256);
+    const size_t o_idx = off; off += align_up((size_t)npix * n_frames, 256);
+    const size_t o_bnd = off; off += align_up(sizeof(uint32_t) * (size_t)W.nb32 * w * n_frames, 256);
+    const size_t o_bb = off; off += align_up(sizeof(uint32_t) * (size_t)W.nbands * n_frames, 256);
+    if (phases & 1) B2_CUDA(ctx, ctx->sixel_work.reserve(off));
+    if (!ctx->sixel_work.p || ctx->sixel_work.cap < off) return ctx->fail(B200TIMG_EINVAL, "sixel: write phase without prepare");
+    ctx->sixel_idx_off = o_idx;
+    char *base = ctx->sixel_work.as<char>();
+    W.hdr = reinterpret_cast<SixelFrameHdr *>(base + o_hdr);
+    W.ent_a = reinterpret_cast<uint32_t *>(base + o_ea); W.ent_b = reinterpret_cast<uint32_t *>(base + o_eb);
+    W.lut = reinterpret_cast<uint8_t *>(base + o_lut); W.index = reinterpret_cast<uint8_t *>(base + o_idx);
+    W.boundary = reinterpret_cast<uint32_t *>(base + o_bnd); W.band_bytes = reinterpret_cast<uint32_t *>(base + o_bb);
+    const uint32_t *fb = reinterpret_cast<const uint32_t *>(d_fb);
+
+    static bool attrs_set = false;
+    EmitGeom G; G.w = w; G.h = h; G.words = (w + 31) / 32; G.chunks = (w + 63) / 64;
+    const size_t smem_limit = 227 * 1024 - 2048;
+    G.group = 256;
+    auto emit_smem = [&](int grp) { return sizeof(uint32_t) * ((size_t)6 * w + (size_t)grp * (G.words + G.chunks)); };
+    while (G.group > 8 && emit_smem(G.group) > smem_limit) G.group >>= 1;
+    if (emit_smem(G.group) > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d)", w);
+    if (!attrs_set) {
+        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+        attrs_set = true;
+    }
+    const dim3 egrid(W.nbands, n_frames);
+    if (phases & 1) {
+    sixel_palette_kernel<<<n_frames, PT, 65536, ctx->stream>>>(fb, w, h, W);
+    B2_LAUNCH_CHECK(ctx);
+    sixel_lut_kernel<<<dim3(128, n_frames), 256, 0, ctx->stream>>>(W);
+    B2_LAUNCH_CHECK(ctx);
+    {
+        long long blocks = (npix + 255) / 256; if (blocks > 64) blocks = 64;
+        sixel_map_kernel<<<dim3((unsigned)blocks, n_frames), 256, 0, ctx->stream>>>(fb, npix, W);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    sixel_dither_kernel<<<n_frames, DW * 32, 32768, ctx->stream>>>(fb, w, h, W);
+    B2_LAUNCH_CHECK(ctx);
+    sixel_emit_kernel<false><<<egrid, ET, emit_smem(G.group), ctx->stream>>>(G, W, nullptr, nullptr, 0);
+    B2_LAUNCH_CHECK(ctx);
+    sixel_layout_kernel<<<n_frames, 256, 0, ctx->stream>>>(w, h, W);
+    B2_LAUNCH_CHECK(ctx);
+    sixel_sizes_to_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(W.hdr, n_frames, d_offsets);
+    B2_LAUNCH_CHECK(ctx);
+    }
+    if (!(phases & 2)) return B200TIMG_OK;
+    sixel_emit_kernel<true><<<egrid, ET, emit_smem(G.group), ctx->stream>>>(G, W, d_offsets, d_out, (unsigned long long)out_cap);
+    B2_LAUNCH_CHECK(ctx);
+    return B200TIMG_OK;
+}
+
+// Introspection for tests: palette, colour counts and index plane of frame 0 of the last encode.
+int sixel_debug_fetch(b200timg_ctx *ctx, uint32_t *h_palette, uint32_t *h_counts, uint8_t *h_index, size_t index_bytes) {
+    if (!ctx->sixel_work.p) return ctx->fail(B200TIMG_EINVAL, "sixel: nothing encoded yet");
+    SixelFrameHdr host;
+    B2_CUDA(ctx, cudaMemcpyAsync(&host, ctx->sixel_work.p, sizeof host, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_index && index_bytes)
+        B2_CUDA(ctx, cudaMemcpyAsync(h_index, ctx->sixel_work.as<char>() + ctx->sixel_idx_off, index_bytes,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_palette) memcpy(h_palette, host.palette, sizeof host.palette);
+    if (h_counts) { h_counts[0] = host.ncolors; h_counts[1] = host.origcolors; }
+    return B200TIMG_OK;
+}
+
+}  // namespace b200timg
