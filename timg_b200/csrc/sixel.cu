@@ -334,6 +334,7 @@ sixel_dither_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W) 
                 __syncwarp();
             }
             const int x = t - 2 * lane;
+            if (t == 0 && lane == 0 && bin) up_p1 = __ldcg(bin);   // e(0, y-1): lane 0 has no warm-up step
             uint32_t recv = __shfl_up_sync(0xffffffffu, last_e, 1);
             if (lane == 0) recv = (bin && x + 1 < w) ? __ldcg(bin + x + 1) : EZ;
             up_m1 = up_0; up_0 = up_p1; up_p1 = recv;
