@@ -173,6 +173,18 @@ int b200timg_compose_dev(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_f
                          int has_bg, uint32_t bg, uint32_t pattern, int pattern_w,
                          int pattern_h, int start_row);
 
+/* The sixel stage alone on n device-resident frames that are already scaled, padded to a
+ * multiple of 6 rows and composed (e.g. BASELINE config 5: 1280x720 frames shown unscaled). */
+int b200timg_sixel_dev(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames,
+                       char *d_out, size_t out_cap, uint64_t *d_offsets);
+
+/* Per-kernel timing with CUDA events recorded on the ctx stream around every launch.
+ * profile(ctx,1) clears and starts, profile(ctx,0) stops and clears.  The report is text, one
+ * line per kernel: "<name> <launches> <total_ms>".  Timing adds two event records per launch,
+ * so throughput numbers are taken with profiling off. */
+int b200timg_profile(b200timg_ctx *ctx, int enable);
+int b200timg_profile_report(b200timg_ctx *ctx, char *buf, size_t cap);
+
 /* Introspection for tests: after b200timg_sixel_encode, the palette (256 words r|g<<8|b<<16),
  * counts[0] = palette entries in use, counts[1] = occupied 15-bit histogram cells, and the
  * palette-index plane (w*h bytes) of that frame.  Any pointer may be NULL. */

@@ -68,6 +68,10 @@ ABI = {
                                      C.c_int, C.c_int]),
     "b200timg_compose_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                        C.c_uint32, C.c_int, C.c_int, C.c_int]),
+    "b200timg_sixel_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]),
+    "b200timg_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200timg_profile_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "b200timg_sixel_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200timg_resample_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -217,6 +221,19 @@ class Context:
             rc = lib().b200timg_sixel_encode(self.h, _np_ptr(fb), w, h, buf, cap, C.byref(n))
         self._chk(rc)
         return buf.raw[:n.value]
+
+    def profile(self, enable=True):
+        self._chk(lib().b200timg_profile(self.h, int(enable)))
+
+    def profile_report(self):
+        """{kernel name: (launches, total_ms)} since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._chk(lib().b200timg_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n), float(ms))
+        return out
 
     def sixel_debug(self, w, h):
         """(palette[n,3] uint8, origcolors, index[h,w]) of the last sixel_encode call."""

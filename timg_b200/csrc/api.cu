@@ -72,6 +72,46 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
 const char *b200timg_last_error(const b200timg_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
 uint64_t b200timg_kernel_launches(const b200timg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// ---- per-kernel timing --------------------------------------------------------------------
+int b200timg_profile(b200timg_ctx *ctx, int enable) {
+    if (!ctx) return B200TIMG_EINVAL;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.begin); cudaEventDestroy(r.end); }
+    ctx->prof.clear();
+    ctx->profiling = enable != 0;
+    return B200TIMG_OK;
+}
+
+int b200timg_profile_report(b200timg_ctx *ctx, char *buf, size_t cap) {
+    if (!ctx || !buf || cap < 2) return B200TIMG_EINVAL;
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    struct Agg { const char *name; int n; double ms; };
+    std::vector<Agg> agg;
+    for (auto &r : ctx->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.begin, r.end) != cudaSuccess) { cudaGetLastError(); continue; }
+        bool found = false;
+        for (auto &a : agg) if (strcmp(a.name, r.name) == 0) { a.n++; a.ms += ms; found = true; break; }
+        if (!found) agg.push_back({r.name, 1, (double)ms});
+    }
+    size_t pos = 0;
+    for (auto &a : agg) {
+        const int n = snprintf(buf + pos, cap - pos, "%s %d %.6f\n", a.name, a.n, a.ms);
+        if (n < 0 || (size_t)n >= cap - pos) return ctx->fail(B200TIMG_ENOSPC, "profile report truncated");
+        pos += (size_t)n;
+    }
+    buf[pos] = 0;
+    return B200TIMG_OK;
+}
+
+// Encode n device-resident, already scaled + padded + composed frames (w x h, h % 6 == 0).
+int b200timg_sixel_dev(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
+                       size_t out_cap, uint64_t *d_offsets) {
+    B2_TRY(check_ctx(ctx));
+    if (!d_fb || !d_out || !d_offsets || w <= 0 || h <= 0 || n_frames <= 0) return ctx->fail(B200TIMG_EINVAL, "sixel_dev: bad args");
+    return launch_sixel(ctx, d_fb, w, h, n_frames, d_out, out_cap, d_offsets, 3);
+}
+
 // ---- geometry: ImageSource::CalcScaleToFitDisplay, src/image-source.cc:47-153 ------------
 int b200timg_calc_fit(const b200timg_fit_opts *o, int img_w, int img_h, int rotated,
                       int *target_w, int *target_h) {

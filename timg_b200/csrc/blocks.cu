@@ -477,14 +477,18 @@ int launch_blocks(b200timg_ctx *ctx, const uint8_t *d_fb, const uint8_t *d_prev,
     FrameRec *frames = reinterpret_cast<FrameRec *>(rows + n_rows);
 
     const dim3 grid(P.rows, n_frames);
+    B2_KERNEL(ctx, "blocks_pick_kernel");
     blocks_pick_kernel<<<grid, BT, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(d_fb),
                                                      reinterpret_cast<const uint32_t *>(d_prev), P, cells, rows);
     B2_LAUNCH_CHECK(ctx);
+    B2_KERNEL(ctx, "blocks_rowscan_kernel");
     blocks_rowscan_kernel<<<n_frames, BT, 0, ctx->stream>>>(P, rows, frames);
     B2_LAUNCH_CHECK(ctx);
+    B2_KERNEL(ctx, "sizes_to_offsets_kernel");
     sizes_to_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(frames),
                                                          sizeof(FrameRec) / 4, n_frames, d_offsets);
     B2_LAUNCH_CHECK(ctx);
+    B2_KERNEL(ctx, "blocks_emit_kernel");
     blocks_emit_kernel<<<grid, BT, 0, ctx->stream>>>(P, cells, rows, frames, d_offsets, d_out,
                                                      (unsigned long long)out_cap);
     B2_LAUNCH_CHECK(ctx);

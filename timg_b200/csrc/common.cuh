@@ -61,6 +61,11 @@ struct b200timg_ctx {
     int sm_count = 148;
     uint64_t launches = 0;
     char err[512] = {0};
+    // optional per-kernel timing (b200timg_profile): CUDA events on the launching stream
+    bool profiling = false;
+    const char *pending_kernel = "?";
+    struct ProfRec { const char *name; cudaEvent_t begin, end; };
+    std::vector<ProfRec> prof;
 
     // scratch, grown on demand
     b200timg::DevBuf in_stage;     // uploaded source frames (host entry points)
@@ -94,13 +99,28 @@ struct b200timg_ctx {
                                cudaGetErrorString(e__));                           \
     } while (0)
 
+#define B2_KERNEL(ctx, kname)                                                      \
+    do {                                                                           \
+        (ctx)->pending_kernel = (kname);                                           \
+        if ((ctx)->profiling) {                                                    \
+            b200timg_ctx::ProfRec r__;                                             \
+            r__.name = (kname);                                                    \
+            cudaEventCreate(&r__.begin); cudaEventCreate(&r__.end);                \
+            cudaEventRecord(r__.begin, (ctx)->stream);                             \
+            (ctx)->prof.push_back(r__);                                            \
+        }                                                                          \
+    } while (0)
+
 #define B2_LAUNCH_CHECK(ctx)                                                       \
     do {                                                                           \
         (ctx)->launches++;                                                         \
+        if ((ctx)->profiling && !(ctx)->prof.empty())                              \
+            cudaEventRecord((ctx)->prof.back().end, (ctx)->stream);                \
         cudaError_t e__ = cudaGetLastError();                                      \
         if (e__ != cudaSuccess)                                                    \
-            return (ctx)->fail(B200TIMG_ECUDA, "%s:%d kernel launch -> %s",        \
-                               __FILE__, __LINE__, cudaGetErrorString(e__));       \
+            return (ctx)->fail(B200TIMG_ECUDA, "%s:%d kernel %s launch -> %s",     \
+                               __FILE__, __LINE__, (ctx)->pending_kernel,          \
+                               cudaGetErrorString(e__));                           \
     } while (0)
 
 #define B2_TRY(expr)                          \

@@ -112,6 +112,7 @@ int launch_compose(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_frames,
         const long long cap = (long long)ctx->sm_count * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
+        B2_KERNEL(ctx, "compose_kernel");
         compose_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
             reinterpret_cast<uint32_t *>(d_fb), P, quads);
     } else {
@@ -119,6 +120,7 @@ int launch_compose(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_frames,
         const long long cap = (long long)ctx->sm_count * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
+        B2_KERNEL(ctx, "compose_kernel_scalar");
         compose_kernel_scalar<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
             reinterpret_cast<uint32_t *>(d_fb), P, total_px);
     }
@@ -133,6 +135,7 @@ int launch_has_transparency(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h
     if (start >= end) return B200TIMG_OK;
     long long blocks = (end - start + 255) / 256;
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    B2_KERNEL(ctx, "transparency_kernel");
     transparency_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(
         reinterpret_cast<const uint32_t *>(d_fb), start, end, d_flag);
     B2_LAUNCH_CHECK(ctx);

@@ -190,10 +190,12 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
     if (pl->copy_only) {
         long long blocks = ((long long)ow * oh * n_frames + 255) / 256;
         if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
+        B2_KERNEL(ctx, "resample_copy_kernel");
         resample_copy_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, P);
     } else {
         if (n_frames > 65535) return ctx->fail(B200TIMG_EINVAL, "scale: too many frames for one launch");
         const dim3 grid((ow + 31) / 32, (oh + 7) / 8, n_frames);
+        B2_KERNEL(ctx, "resample_direct_kernel");
         if (pl->vertical_first) resample_direct_kernel<true><<<grid, 256, 0, ctx->stream>>>(in, out, P);
         else resample_direct_kernel<false><<<grid, 256, 0, ctx->stream>>>(in, out, P);
     }

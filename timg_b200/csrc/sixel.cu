@@ -669,25 +669,33 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     }
     const dim3 egrid(W.nbands, n_frames);
     if (phases & 1) {
+    B2_KERNEL(ctx, "sixel_palette_kernel");
     sixel_palette_kernel<<<n_frames, PT, 65536, ctx->stream>>>(fb, w, h, W);
     B2_LAUNCH_CHECK(ctx);
+    B2_KERNEL(ctx, "sixel_lut_kernel");
     sixel_lut_kernel<<<dim3(128, n_frames), 256, 0, ctx->stream>>>(W);
     B2_LAUNCH_CHECK(ctx);
     {
         long long blocks = (npix + 255) / 256; if (blocks > 64) blocks = 64;
+        B2_KERNEL(ctx, "sixel_map_kernel");
         sixel_map_kernel<<<dim3((unsigned)blocks, n_frames), 256, 0, ctx->stream>>>(fb, npix, W);
         B2_LAUNCH_CHECK(ctx);
     }
+    B2_KERNEL(ctx, "sixel_dither_kernel");
     sixel_dither_kernel<<<n_frames, DW * 32, 32768, ctx->stream>>>(fb, w, h, W);
     B2_LAUNCH_CHECK(ctx);
+    B2_KERNEL(ctx, "sixel_emit_kernel");
     sixel_emit_kernel<false><<<egrid, ET, emit_smem(G.group), ctx->stream>>>(G, W, nullptr, nullptr, 0);
     B2_LAUNCH_CHECK(ctx);
+    B2_KERNEL(ctx, "sixel_layout_kernel");
     sixel_layout_kernel<<<n_frames, 256, 0, ctx->stream>>>(w, h, W);
     B2_LAUNCH_CHECK(ctx);
+    B2_KERNEL(ctx, "sixel_sizes_to_offsets_kernel");
     sixel_sizes_to_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(W.hdr, n_frames, d_offsets);
     B2_LAUNCH_CHECK(ctx);
     }
     if (!(phases & 2)) return B200TIMG_OK;
+    B2_KERNEL(ctx, "sixel_emit_kernel");
     sixel_emit_kernel<true><<<egrid, ET, emit_smem(G.group), ctx->stream>>>(G, W, d_offsets, d_out, (unsigned long long)out_cap);
     B2_LAUNCH_CHECK(ctx);
     return B200TIMG_OK;
