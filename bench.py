@@ -191,8 +191,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)            # a real (non-default) stream shared by torch and the library,
+    torch.cuda.set_stream(stream)              # so torch's CUDA events time the library's launches
     ctx = timg_b200.Context(local_rank, stream.cuda_stream)
+    assert stream.cuda_stream != 0
     L = timg_b200.lib()
     F = args.frames
     frames = torch.empty((F, IH, IW, 4), dtype=torch.uint8, device=dev)

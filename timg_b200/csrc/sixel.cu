@@ -387,34 +387,64 @@ __device__ __forceinline__ char *put_rle(char *o, uint32_t n, char ch) {
     return o;
 }
 
-constexpr int ET = 512;
-constexpr uint32_t ENT_INVALID = 0xffffffffu;
-// ent word: colour [0:8) | bits [8:14) | bytes [16:24)
+constexpr int ET = 512, EW = ET / 32;
+// sorted entry word: colour [18:26) | x [6:18) | bits [0:6)  -> ascending order == (colour, x)
+__device__ __forceinline__ uint32_t ent_pack(uint32_t c, uint32_t x, uint32_t bits) { return (c << 18) | (x << 6) | bits; }
 
-struct EmitGeom { int w, h, words, chunks, group; };   // words = ceil(w/32), chunks = ceil(w/64), group = colours per pass
+struct EmitGeom { int w, h, cols_per_warp; };
 
-__device__ __forceinline__ uint32_t bits_of(const uint32_t *ent, int w, int x, uint32_t c) {
+// The <=6 distinct (colour, bits) pairs of column x of a 6-row band.
+__device__ __forceinline__ int column_entries(const uint8_t *__restrict__ idx, int w, int x, uint32_t *col, uint32_t *bits) {
+    uint32_t c[6];
 #pragma unroll
-    for (int s = 0; s < 6; ++s) { const uint32_t e = ent[s * w + x]; if (e != ENT_INVALID && (e & 0xff) == c) return (e >> 8) & 63; }
-    return 0;
-}
-__device__ __forceinline__ uint32_t bytes_of(const uint32_t *ent, int w, int x, uint32_t c) {
+    for (int i = 0; i < 6; ++i) c[i] = idx[(long long)i * w + x];
+    int ns = 0;
 #pragma unroll
-    for (int s = 0; s < 6; ++s) { const uint32_t e = ent[s * w + x]; if (e != ENT_INVALID && (e & 0xff) == c) return (e >> 16) & 0xff; }
-    return 0;
+    for (int i = 0; i < 6; ++i) {
+        bool seen = false;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) if (j < i && c[j] == c[i]) seen = true;
+        uint32_t b = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) if (j >= i && c[j] == c[i]) b |= 1u << j;
+        if (!seen) { col[ns] = c[i]; bits[ns] = b; ++ns; }
+    }
+    return ns;
 }
 
+// bytes the entry at sorted position i contributes (0 unless it starts a run); also returns the
+// pieces the writer needs.
+struct RunInfo { uint32_t bytes, gap, len, c, bits; bool first_of_colour; };
+__device__ __forceinline__ RunInfo run_info(const uint32_t *sorted, int i, int n, uint32_t minc) {
+    RunInfo r;
+    const uint32_t e = sorted[i];
+    r.c = e >> 18; r.bits = e & 63;
+    const uint32_t x = (e >> 6) & 4095;
+    const bool has_prev = i > 0 && (sorted[i - 1] >> 18) == r.c;
+    const uint32_t p = has_prev ? sorted[i - 1] : 0;
+    r.first_of_colour = !has_prev;
+    r.bytes = 0; r.gap = 0; r.len = 0;
+    if (has_prev && ((p >> 6) & 4095) == x - 1 && (p & 63) == r.bits) return r;      // continues the previous run
+    uint32_t L = 1;
+    while (i + (int)L < n && sorted[i + L] == e + (L << 6)) ++L;                     // same colour, x+L, same bits
+    r.len = L;
+    r.gap = has_prev ? x - ((p >> 6) & 4095) - 1 : x;
+    r.bytes = rle_len(r.gap) + rle_len(L) + (has_prev ? 0 : 1 + ndig_u(r.c) + (r.c != minc ? 1 : 0));
+    return r;
+}
+
+// One CTA per 6-row band.  (1) per-warp counting sort of the band's (colour, x, bits) entries by
+// colour -- warps own contiguous column ranges, so warp-major order is x order and the sort is
+// stable; (2) every run head sizes its "gap + run" bytes, block scan -> offsets; (3) WRITE: bytes.
 template <bool WRITE>
 __global__ void __launch_bounds__(ET)
 sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets, char *__restrict__ out,
                   unsigned long long out_cap) {
-    extern __shared__ uint32_t s_mem[];
-    uint32_t *ent = s_mem;                                   // [6][w]
-    uint32_t *P = ent + 6 * G.w;                             // [group][words]
-    uint32_t *S = P + G.group * G.words;                     // [group][chunks]
+    extern __shared__ uint32_t s_sorted[];                   // [6*w]
+    __shared__ unsigned short s_cnt[EW][256];
     __shared__ uint32_t s_w[ET / 32];
-    __shared__ uint32_t s_minc, s_run;
-    const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    __shared__ uint32_t s_colbase[256];
+    const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int w = G.w;
     const SixelFrameHdr *hdr = W.hdr + f;
     const uint8_t *idx = W.index + ((long long)f * G.h + (long long)band * 6) * w;
@@ -425,38 +455,12 @@ sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets,
         if (fbase + hdr->frame_size > out_cap) return;       // never write out of bounds
         band_off = W.band_bytes[(long long)f * W.nbands + band];
     }
-    if (tid == 0) { s_minc = 256; s_run = 0; }
+    for (int i = tid; i < EW * 256; i += ET) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
-    // distinct (colour, bits) pairs of every column of this 6-row band
-    uint32_t my_min = 256;
-    for (int x = tid; x < w; x += ET) {
-        uint32_t c[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) c[i] = idx[(long long)i * w + x];
-        int ns = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            bool seen = false;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) if (j < i && c[j] == c[i]) seen = true;
-            if (!seen) {
-                uint32_t bits = 0;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) if (j >= i && c[j] == c[i]) bits |= 1u << j;
-                ent[ns * w + x] = c[i] | (bits << 8);
-                my_min = min(my_min, c[i]);
-                ++ns;
-            }
-        }
-        for (; ns < 6; ++ns) ent[ns * w + x] = ENT_INVALID;
-    }
-    atomicMin(&s_minc, my_min);
-    __syncthreads();
-    const uint32_t minc = s_minc;
 
     if (WRITE && band == 0) {                                // header: DCS q, raster attributes, palette
-        char *o = out + fbase;
         if (tid == 0) {
+            char *o = out + fbase;
             *o++ = '\033'; *o++ = 'P'; *o++ = 'q'; *o++ = '"'; *o++ = '1'; *o++ = ';'; *o++ = '1'; *o++ = ';';
             o = put_num_u(o, (uint32_t)w); *o++ = ';'; o = put_num_u(o, (uint32_t)G.h);
         }
@@ -479,89 +483,86 @@ sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets,
         if (band == W.nbands - 1) { out[fbase + hdr->frame_size - 2] = '\033'; out[fbase + hdr->frame_size - 1] = '\\'; }
     }
 
-    for (int g0 = 0; g0 < 256; g0 += G.group) {
-        for (int i = tid; i < G.group * (G.words + G.chunks); i += ET) P[i] = 0;   // P and S are contiguous
-        __syncthreads();
-        for (int x = tid; x < w; x += ET)
+    // (1a) count entries per (warp, colour)
+    const int x_lo = wid * G.cols_per_warp, x_hi = min(w, x_lo + G.cols_per_warp);
+    for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
+        const int x = x0 + lane;
+        uint32_t col[6], bits[6];
+        const int ns = x < x_hi ? column_entries(idx, w, x, col, bits) : 0;
 #pragma unroll
-            for (int s = 0; s < 6; ++s) {
-                const uint32_t e = ent[s * w + x];
-                if (e == ENT_INVALID) break;
-                const int c = (int)(e & 0xff) - g0;
-                if (c >= 0 && c < G.group) atomicOr(&P[c * G.words + (x >> 5)], 1u << (x & 31));
+        for (int s = 0; s < 6; ++s) {
+            const bool have = s < ns;
+            const uint32_t vm = __ballot_sync(0xffffffffu, have);
+            if (have) {
+                const uint32_t m = __match_any_sync(vm, col[s]);
+                if ((m & ((1u << lane) - 1)) == 0) s_cnt[wid][col[s]] += (unsigned short)__popc(m);
             }
-        __syncthreads();
-        for (int x = tid; x < w; x += ET)
-#pragma unroll
-            for (int s = 0; s < 6; ++s) {
-                const uint32_t e = ent[s * w + x];
-                if (e == ENT_INVALID) break;
-                const uint32_t c = e & 0xff;
-                const int cg = (int)c - g0;
-                if (cg < 0 || cg >= G.group) continue;
-                const uint32_t bits = (e >> 8) & 63;
-                const uint32_t *Pc = P + cg * G.words;
-                int j = x >> 5;
-                uint32_t m = Pc[j] & ((1u << (x & 31)) - 1);
-                while (m == 0 && --j >= 0) m = Pc[j];
-                const int px = m ? j * 32 + 31 - __clz(m) : -1;
-                uint32_t bytes = 0;
-                if (!(px == x - 1 && bits_of(ent, w, px, c) == bits)) {        // head of a run
-                    uint32_t L = 1; int nx = x + 1;
-                    while (nx < w && ((Pc[nx >> 5] >> (nx & 31)) & 1) && bits_of(ent, w, nx, c) == bits) { ++L; ++nx; }
-                    bytes = rle_len((uint32_t)(x - px - 1)) + rle_len(L);
-                    if (px < 0) bytes += 1 + ndig_u(c) + (c != minc ? 1 : 0);   // "#c", preceded by '$' unless first row
-                    atomicAdd(&S[cg * G.chunks + (x >> 6)], bytes);
-                }
-                ent[s * w + x] = (e & 0xffff) | (bytes << 16);
-            }
-        __syncthreads();
-        // exclusive scan of S in colour-major order (each thread owns a contiguous slice)
-        const int nS = G.group * G.chunks, per = (nS + ET - 1) / ET;
-        const int lo = tid * per, hi = min(nS, lo + per);
-        uint32_t local = 0;
-        for (int i = lo; i < hi; ++i) local += S[i];
-        uint32_t gtot; uint32_t at = block_excl_scan<ET>(local, s_w, gtot);
-        for (int i = lo; i < hi; ++i) { const uint32_t v = S[i]; S[i] = at; at += v; }
-        __syncthreads();
-        if (WRITE) {
-            const uint32_t run = s_run;
-            for (int x = tid; x < w; x += ET)
-#pragma unroll
-                for (int s = 0; s < 6; ++s) {
-                    const uint32_t e = ent[s * w + x];
-                    if (e == ENT_INVALID) break;
-                    const uint32_t c = e & 0xff, bytes = (e >> 16) & 0xff;
-                    const int cg = (int)c - g0;
-                    if (cg < 0 || cg >= G.group || bytes == 0) continue;
-                    const uint32_t bits = (e >> 8) & 63;
-                    const uint32_t *Pc = P + cg * G.words;
-                    uint32_t off = run + S[cg * G.chunks + (x >> 6)];
-                    int px = -1;
-                    {   // earlier entries of this colour inside the same 64-column chunk
-                        const int j0 = (x >> 6) * 2, jx = x >> 5;
-                        for (int j = j0; j <= jx; ++j) {
-                            uint32_t m = Pc[j];
-                            if (j == jx) m &= (1u << (x & 31)) - 1;
-                            while (m) { const int b = __ffs(m) - 1; m &= m - 1; off += bytes_of(ent, w, j * 32 + b, c); }
-                        }
-                        int j = jx; uint32_t m = Pc[j] & ((1u << (x & 31)) - 1);
-                        while (m == 0 && --j >= 0) m = Pc[j];
-                        px = m ? j * 32 + 31 - __clz(m) : -1;
-                    }
-                    uint32_t L = 1; int nx = x + 1;
-                    while (nx < w && ((Pc[nx >> 5] >> (nx & 31)) & 1) && bits_of(ent, w, nx, c) == bits) { ++L; ++nx; }
-                    char *o = out + fbase + band_off + off;
-                    if (px < 0) { if (c != minc) *o++ = '$'; *o++ = '#'; o = put_num_u(o, c); }
-                    o = put_rle(o, (uint32_t)(x - px - 1), '?');
-                    o = put_rle(o, L, (char)('?' + bits));
-                }
+            __syncwarp();
         }
-        __syncthreads();
-        if (tid == 0) s_run += gtot;
-        __syncthreads();
     }
-    if (!WRITE && tid == 0) W.band_bytes[(long long)f * W.nbands + band] = s_run;
+    __syncthreads();
+    // per-colour totals -> colour bases -> per (warp, colour) start offsets (in place)
+    uint32_t tot_c = 0;
+    if (tid < 256) for (int k = 0; k < EW; ++k) tot_c += s_cnt[k][tid];
+    uint32_t n_ent; const uint32_t cb = block_excl_scan<ET>(tid < 256 ? tot_c : 0, s_w, n_ent);
+    if (tid < 256) {
+        s_colbase[tid] = cb;
+        uint32_t run = cb;
+        for (int k = 0; k < EW; ++k) { const uint32_t v = s_cnt[k][tid]; s_cnt[k][tid] = (unsigned short)run; run += v; }
+    }
+    __syncthreads();
+    // (1b) scatter
+    for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
+        const int x = x0 + lane;
+        uint32_t col[6], bits[6];
+        const int ns = x < x_hi ? column_entries(idx, w, x, col, bits) : 0;
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+            const bool have = s < ns;
+            const uint32_t vm = __ballot_sync(0xffffffffu, have);
+            if (have) {
+                const uint32_t m = __match_any_sync(vm, col[s]);
+                const uint32_t below = __popc(m & ((1u << lane) - 1));
+                const uint32_t at = s_cnt[wid][col[s]];
+                s_sorted[at + below] = ent_pack(col[s], (uint32_t)x, bits[s]);
+                __syncwarp(vm);
+                if (below == 0) s_cnt[wid][col[s]] = (unsigned short)(at + __popc(m));
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // Inside one 32-column step a colour may sit in different slots of different columns, so a
+    // (warp, colour) segment is ordered by (step, slot, lane) rather than by x: sort each of the
+    // EW*256 tiny segments (packed words compare as (colour, x)).
+    for (int seg = tid; seg < EW * 256; seg += ET) {
+        const int c = seg & 255, k = seg >> 8;
+        const int beg = k > 0 ? s_cnt[k - 1][c] : (int)s_colbase[c], end = s_cnt[k][c];
+        for (int i = beg + 1; i < end; ++i) {
+            const uint32_t v = s_sorted[i];
+            int j = i - 1;
+            while (j >= beg && s_sorted[j] > v) { s_sorted[j + 1] = s_sorted[j]; --j; }
+            s_sorted[j + 1] = v;
+        }
+    }
+    __syncthreads();
+    // (2) sizes
+    const int n = (int)n_ent;
+    const uint32_t minc = s_sorted[0] >> 18;
+    const int per = (n + ET - 1) / ET, lo = min(n, tid * per), hi = min(n, lo + per);
+    uint32_t local = 0;
+    for (int i = lo; i < hi; ++i) local += run_info(s_sorted, i, n, minc).bytes;
+    uint32_t band_total; uint32_t at = block_excl_scan<ET>(local, s_w, band_total);
+    if (!WRITE) { if (tid == 0) W.band_bytes[(long long)f * W.nbands + band] = band_total; return; }
+    // (3) bytes
+    char *o = out + fbase + band_off + at;
+    for (int i = lo; i < hi; ++i) {
+        const RunInfo r = run_info(s_sorted, i, n, minc);
+        if (!r.bytes) continue;
+        if (r.first_of_colour) { if (r.c != minc) *o++ = '$'; *o++ = '#'; o = put_num_u(o, r.c); }
+        o = put_rle(o, r.gap, '?');
+        o = put_rle(o, r.len, (char)('?' + r.bits));
+    }
 }
 
 // per frame: header length, band offsets (exclusive, in place), frame size
@@ -655,12 +656,10 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     const uint32_t *fb = reinterpret_cast<const uint32_t *>(d_fb);
 
     static bool attrs_set = false;
-    EmitGeom G; G.w = w; G.h = h; G.words = (w + 31) / 32; G.chunks = (w + 63) / 64;
-    const size_t smem_limit = 227 * 1024 - 2048;
-    G.group = 256;
-    auto emit_smem = [&](int grp) { return sizeof(uint32_t) * ((size_t)6 * w + (size_t)grp * (G.words + G.chunks)); };
-    while (G.group > 8 && emit_smem(G.group) > smem_limit) G.group >>= 1;
-    if (emit_smem(G.group) > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d)", w);
+    EmitGeom G; G.w = w; G.h = h; G.cols_per_warp = ((w + EW - 1) / EW + 31) / 32 * 32;
+    const size_t smem_limit = 227 * 1024 - 16 * 1024;
+    const size_t emit_smem = sizeof(uint32_t) * (size_t)6 * w;
+    if (w > 4095 || emit_smem > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
     if (!attrs_set) {
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
@@ -685,7 +684,7 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     sixel_dither_kernel<<<n_frames, DW * 32, 32768, ctx->stream>>>(fb, w, h, W);
     B2_LAUNCH_CHECK(ctx);
     B2_KERNEL(ctx, "sixel_emit_kernel");
-    sixel_emit_kernel<false><<<egrid, ET, emit_smem(G.group), ctx->stream>>>(G, W, nullptr, nullptr, 0);
+    sixel_emit_kernel<false><<<egrid, ET, emit_smem, ctx->stream>>>(G, W, nullptr, nullptr, 0);
     B2_LAUNCH_CHECK(ctx);
     B2_KERNEL(ctx, "sixel_layout_kernel");
     sixel_layout_kernel<<<n_frames, 256, 0, ctx->stream>>>(w, h, W);
@@ -696,7 +695,7 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     }
     if (!(phases & 2)) return B200TIMG_OK;
     B2_KERNEL(ctx, "sixel_emit_kernel");
-    sixel_emit_kernel<true><<<egrid, ET, emit_smem(G.group), ctx->stream>>>(G, W, d_offsets, d_out, (unsigned long long)out_cap);
+    sixel_emit_kernel<true><<<egrid, ET, emit_smem, ctx->stream>>>(G, W, d_offsets, d_out, (unsigned long long)out_cap);
     B2_LAUNCH_CHECK(ctx);
     return B200TIMG_OK;
 }
