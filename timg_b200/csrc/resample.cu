@@ -8,6 +8,8 @@
 //
 // v1 layout: one thread per output pixel, taps read straight from global memory (the
 // working set of a tile stays in L1/L2).  Algorithmic bytes: 4*iw*ih read + 4*ow*oh written.
+#include <algorithm>
+
 #include "common.cuh"
 #include "resample_tables.h"
 
@@ -120,6 +122,201 @@ resample_direct_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
     out[((long long)f * P.out_frame_rows + oy) * P.ow + ox] = encode_px(res);
 }
 
+// ---- tiled separable kernel ---------------------------------------------------------------
+// One CTA produces a TW x TH output tile.  The input window the tile needs is decoded ONCE into
+// shared memory as float4 pixels, the first pass (vertical or horizontal, whichever the
+// reference's cost model picks) writes a float4 intermediate tile to shared memory, the second
+// pass reads it.  Arithmetic and summation order are exactly those of resample_direct_kernel;
+// only the sharing of partial sums between neighbouring output pixels is new.
+// Only 4 of the 7 channels are carried (A, R*A, G*A, B*A): the un-weighted R,G,B are needed only
+// where the filtered alpha is < 2^-120 (fully transparent output), and tiles that contain such a
+// pixel run a second pass for them.
+struct TileGeom { int tw, th, nix_max, niy_max; };
+
+__device__ __forceinline__ float4 decode_pm(uint32_t p, int bgra) {       // (R*A, G*A, B*A, A)
+    const float k = 1.0f / 255.0f;
+    const float c0 = fmul((float)(p & 0xff), k), c1 = fmul((float)((p >> 8) & 0xff), k);
+    const float c2 = fmul((float)((p >> 16) & 0xff), k), a = fmul((float)(p >> 24), k);
+    const float r = bgra ? c2 : c0, b = bgra ? c0 : c2;
+    return make_float4(fmul(r, a), fmul(c1, a), fmul(b, a), a);
+}
+__device__ __forceinline__ float4 decode_plain(uint32_t p, int bgra) {    // (R, G, B, -)
+    const float k = 1.0f / 255.0f;
+    const float c0 = fmul((float)(p & 0xff), k), c1 = fmul((float)((p >> 8) & 0xff), k);
+    const float c2 = fmul((float)((p >> 16) & 0xff), k);
+    return make_float4(bgra ? c2 : c0, c1, bgra ? c0 : c2, 0.0f);
+}
+__device__ __forceinline__ float4 mul4(float4 v, float w) { return make_float4(fmul(v.x, w), fmul(v.y, w), fmul(v.z, w), fmul(v.w, w)); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z), fadd(a.w, b.w)); }
+
+constexpr int RT = 256;      // threads per tile CTA
+constexpr int RPPT = 4;      // max output pixels per thread (TW*TH <= RT*RPPT)
+
+// Tap loops.  HW / VW > 0: compile-time tap budget (taps beyond an output's own count are skipped
+// by predicate, the loop is fully unrolled); 0: run-time loop.  Horizontal taps go alternately to
+// two accumulators and the two are added at the end -- which accumulator gets the even taps does
+// not matter because IEEE addition is commutative, so the reference's "leading zero taps" (which
+// only flip that assignment) need no special handling here.
+template <int VW>
+__device__ __forceinline__ float4 vsum(const float4 *col, int stride, int cnt, const float *vc) {
+    float4 a = mul4(col[0], vc[0]);
+    if (VW > 0) {
+#pragma unroll
+        for (int k = 1; k < VW; ++k) if (k < cnt) a = add4(a, mul4(col[k * stride], vc[k]));
+    } else {
+        for (int k = 1; k < cnt; ++k) a = add4(a, mul4(col[k * stride], vc[k]));
+    }
+    return a;
+}
+template <int HW>
+__device__ __forceinline__ float4 hsum(const float4 *row, int cnt, const float *hc, bool sequential) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a0 = z, a1 = z;
+    if (sequential) {
+        a0 = mul4(row[0], hc[0]);
+#pragma unroll
+        for (int i = 1; i < 3; ++i) if (i < cnt) a0 = add4(a0, mul4(row[i], hc[i]));
+        return a0;
+    }
+    if (HW > 0) {
+#pragma unroll
+        for (int i = 0; i < HW; ++i) if (i < cnt) { const float4 t = mul4(row[i], hc[i]); if (i & 1) a1 = add4(a1, t); else a0 = add4(a0, t); }
+    } else {
+        for (int i = 0; i < cnt; ++i) { const float4 t = mul4(row[i], hc[i]); if (i & 1) a1 = add4(a1, t); else a0 = add4(a0, t); }
+    }
+    return add4(a0, a1);
+}
+
+template <bool VFIRST, int HW, int VW>
+__global__ void __launch_bounds__(RT)
+resample_tiled_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, TileGeom G) {
+    extern __shared__ float4 s_px[];                  // Din[niy][nix], T, then the tile's tap tables
+    __shared__ int s_ext[4];                          // ix0, ix1, iy0, iy1
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.z;
+    const int ox0 = blockIdx.x * G.tw, oy0 = blockIdx.y * G.th;
+    const int tw = min(G.tw, P.ow - ox0), th = min(G.th, P.oh - oy0);
+    const int dstride = G.nix_max;
+    float4 *Din = s_px;
+    float4 *T = s_px + (size_t)G.niy_max * dstride;
+    const int t_elems = VFIRST ? G.th * dstride : G.niy_max * G.tw;
+    int *s_hmeta = reinterpret_cast<int *>(T + t_elems);           // [tw][2] first, count
+    int *s_vmeta = s_hmeta + 2 * G.tw;                             // [th][2]
+    const int hstride = P.h_widest | 1, vstride = P.v_widest | 1;  // odd: conflict-free
+    float *s_hc = reinterpret_cast<float *>(s_vmeta + 2 * G.th);   // [tw][hstride]
+    float *s_vc = s_hc + G.tw * hstride;                           // [th][vstride]
+    if (tid == 0) { s_ext[0] = 0x7fffffff; s_ext[1] = -1; s_ext[2] = 0x7fffffff; s_ext[3] = -1; }
+    __syncthreads();
+    if (tid < tw) {
+        const int a = P.h_first[ox0 + tid], c = P.h_count[ox0 + tid];
+        s_hmeta[2 * tid] = a; s_hmeta[2 * tid + 1] = c;
+        atomicMin(&s_ext[0], a); atomicMax(&s_ext[1], a + c - 1);
+    }
+    if (tid >= 64 && tid - 64 < th) {
+        const int t = tid - 64, a = P.v_first[oy0 + t], c = P.v_count[oy0 + t];
+        s_vmeta[2 * t] = a; s_vmeta[2 * t + 1] = c;
+        atomicMin(&s_ext[2], a); atomicMax(&s_ext[3], a + c - 1);
+    }
+    for (int e = tid; e < tw * P.h_widest; e += RT) { const int x = e / P.h_widest, i = e - x * P.h_widest; s_hc[x * hstride + i] = P.h_coeff[(long long)(ox0 + x) * P.h_widest + i]; }
+    for (int e = tid; e < th * P.v_widest; e += RT) { const int y = e / P.v_widest, i = e - y * P.v_widest; s_vc[y * vstride + i] = P.v_coeff[(long long)(oy0 + y) * P.v_widest + i]; }
+    __syncthreads();
+    const int ix0 = s_ext[0], nix = s_ext[1] - ix0 + 1, iy0 = s_ext[2], niy = s_ext[3] - iy0 + 1;
+    const uint32_t *src = in + (long long)f * P.iw * P.ih;
+    const bool hseq = P.h_sequential != 0;
+    const float tiny = 7.5231638452626401e-37f;       // 2^-120
+    // this thread's output pixels: one column tx, rows ty0 + q*rstep (they share the horizontal taps)
+    const int tx = tid & (G.tw - 1), ty0 = tid / G.tw, rstep = RT / G.tw;
+    const bool col_ok = tx < tw;
+
+    float4 res[RPPT], plain[RPPT];
+    bool need_plain = false;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int ly = wid; ly < niy; ly += RT / 32) {            // stage + decode once; a warp per row
+            const uint32_t *row = src + (long long)(iy0 + ly) * P.iw + ix0;
+            float4 *drow = Din + ly * dstride;
+            for (int lx = lane; lx < nix; lx += 32) drow[lx] = pass == 0 ? decode_pm(row[lx], P.bgra) : decode_plain(row[lx], P.bgra);
+        }
+        __syncthreads();
+        float4 acc[RPPT];
+        if (VFIRST) {
+            for (int ty = wid; ty < th; ty += RT / 32) {         // T[ty][lx] = sum_k Din[v_first+k][lx]*cv[k], rows in order
+                const int n0 = s_vmeta[2 * ty] - iy0, cnt = s_vmeta[2 * ty + 1];
+                const float *vc = s_vc + ty * vstride;
+                const float4 *dcol = Din + n0 * dstride;
+                float4 *trow = T + ty * dstride;
+                for (int lx = lane; lx < nix; lx += 32) trow[lx] = vsum<VW>(dcol + lx, dstride, cnt, vc);
+            }
+            __syncthreads();
+            if (col_ok) {
+                const int n0 = s_hmeta[2 * tx] - ix0, cnt = s_hmeta[2 * tx + 1];
+                const float *hc = s_hc + tx * hstride;
+#pragma unroll
+                for (int q = 0; q < RPPT; ++q) {
+                    const int ty = ty0 + q * rstep;
+                    if (ty < th) acc[q] = hsum<HW>(T + ty * dstride + n0, cnt, hc, hseq);
+                }
+            }
+        } else {
+            if (col_ok) {                                        // T[ly][tx] = sum_i Din[ly][h_first+i]*ch[i]
+                const int n0 = s_hmeta[2 * tx] - ix0, cnt = s_hmeta[2 * tx + 1];
+                const float *hc = s_hc + tx * hstride;
+                for (int ly = ty0; ly < niy; ly += rstep) T[ly * G.tw + tx] = hsum<HW>(Din + ly * dstride + n0, cnt, hc, hseq);
+            }
+            __syncthreads();
+            if (col_ok) {
+#pragma unroll
+                for (int q = 0; q < RPPT; ++q) {
+                    const int ty = ty0 + q * rstep;
+                    if (ty < th) {
+                        const int n0 = s_vmeta[2 * ty] - iy0, cnt = s_vmeta[2 * ty + 1];
+                        acc[q] = vsum<VW>(T + n0 * G.tw + tx, G.tw, cnt, s_vc + ty * vstride);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RPPT; ++q) { if (pass == 0) res[q] = acc[q]; else plain[q] = acc[q]; }
+        if (pass == 0) {
+#pragma unroll
+            for (int q = 0; q < RPPT; ++q) if (col_ok && ty0 + q * rstep < th && res[q].w < tiny) need_plain = true;
+            if (!__syncthreads_or(need_plain)) break;          // also orders T/Din reuse for pass 1
+        }
+    }
+    if (col_ok) {
+#pragma unroll
+        for (int q = 0; q < RPPT; ++q) {
+            const int ty = ty0 + q * rstep;
+            if (ty < th) {
+                float v[7];
+                v[3] = res[q].w; v[4] = res[q].x; v[5] = res[q].y; v[6] = res[q].z;
+                const bool transparent = res[q].w < tiny;
+                v[0] = transparent ? plain[q].x : 0.f; v[1] = transparent ? plain[q].y : 0.f; v[2] = transparent ? plain[q].z : 0.f;
+                out[((long long)f * P.out_frame_rows + oy0 + ty) * P.ow + ox0 + tx] = encode_px(v);
+            }
+        }
+    }
+}
+
+typedef void (*TiledFn)(const uint32_t *, uint32_t *, ResampleParams, TileGeom);
+template <bool VF, int HW>
+static TiledFn pick_v(int vclass) {
+    switch (vclass) {
+    case 4: return resample_tiled_kernel<VF, HW, 4>;
+    case 6: return resample_tiled_kernel<VF, HW, 6>;
+    case 8: return resample_tiled_kernel<VF, HW, 8>;
+    default: return resample_tiled_kernel<VF, HW, 0>;
+    }
+}
+template <bool VF>
+static TiledFn pick_h(int hclass, int vclass) {
+    switch (hclass) {
+    case 4: return pick_v<VF, 4>(vclass);
+    case 6: return pick_v<VF, 6>(vclass);
+    case 8: return pick_v<VF, 8>(vclass);
+    default: return pick_v<VF, 0>(vclass);
+    }
+}
+static int tap_class(int widest) { return widest <= 4 ? 4 : widest <= 6 ? 6 : widest <= 8 ? 8 : 0; }
+
 // both axes point-sampled (scale 1): plain copy, with the BGRA swizzle if asked (:6938-6940).
 __global__ void __launch_bounds__(256)
 resample_copy_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P) {
@@ -194,10 +391,42 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
         resample_copy_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, P);
     } else {
         if (n_frames > 65535) return ctx->fail(B200TIMG_EINVAL, "scale: too many frames for one launch");
-        const dim3 grid((ow + 31) / 32, (oh + 7) / 8, n_frames);
-        B2_KERNEL(ctx, "resample_direct_kernel");
-        if (pl->vertical_first) resample_direct_kernel<true><<<grid, 256, 0, ctx->stream>>>(in, out, P);
-        else resample_direct_kernel<false><<<grid, 256, 0, ctx->stream>>>(in, out, P);
+        // tile shape: largest of a few candidates whose decoded window + intermediate fit in shared memory
+        static const int cand[][2] = {{64, 16}, {32, 16}, {32, 8}, {16, 8}, {8, 4}};
+        TileGeom G{0, 0, 0, 0};
+        size_t smem = 0;
+        const size_t smem_budget = 74 * 1024;      // 3 CTAs/SM
+        for (const auto &c : cand) {
+            int nix = 1, niy = 1;
+            for (int x0 = 0; x0 < ow; x0 += c[0]) {
+                int lo = 0x7fffffff, hi = -1;
+                for (int x = x0; x < std::min(ow, x0 + c[0]); ++x) { lo = std::min(lo, pl->h.first[x]); hi = std::max(hi, pl->h.first[x] + pl->h.count[x] - 1); }
+                nix = std::max(nix, hi - lo + 1);
+            }
+            for (int y0 = 0; y0 < oh; y0 += c[1]) {
+                int lo = 0x7fffffff, hi = -1;
+                for (int y = y0; y < std::min(oh, y0 + c[1]); ++y) { lo = std::min(lo, pl->v.first[y]); hi = std::max(hi, pl->v.first[y] + pl->v.count[y] - 1); }
+                niy = std::max(niy, hi - lo + 1);
+            }
+            const size_t need = sizeof(float4) * ((size_t)nix * niy + (pl->vertical_first ? (size_t)c[1] * nix : (size_t)niy * c[0]))
+                              + sizeof(int) * (2 * (size_t)c[0] + 2 * (size_t)c[1])
+                              + sizeof(float) * ((size_t)c[0] * (pl->h.widest | 1) + (size_t)c[1] * (pl->v.widest | 1));
+            if (need <= smem_budget || (&c == &cand[4] && need <= 200 * 1024)) { G = TileGeom{c[0], c[1], nix, niy}; smem = need; break; }
+        }
+        if (G.tw) {
+            TiledFn fn = pl->vertical_first ? pick_h<true>(tap_class(pl->h.widest), tap_class(pl->v.widest))
+                                            : pick_h<false>(tap_class(pl->h.widest), tap_class(pl->v.widest));
+            B2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            const dim3 grid((ow + G.tw - 1) / G.tw, (oh + G.th - 1) / G.th, n_frames);
+            B2_KERNEL(ctx, "resample_tiled_kernel");
+            fn<<<grid, RT, smem, ctx->stream>>>(in, out, P, G);
+        } else {
+            // extreme ratios whose window does not fit in shared memory: per-pixel kernel
+            const dim3 grid((ow + 31) / 32, (oh + 7) / 8, n_frames);
+            B2_KERNEL(ctx, "resample_direct_kernel");
+            if (pl->vertical_first) resample_direct_kernel<true><<<grid, 256, 0, ctx->stream>>>(in, out, P);
+            else resample_direct_kernel<false><<<grid, 256, 0, ctx->stream>>>(in, out, P);
+        }
     }
     B2_LAUNCH_CHECK(ctx);
     return B200TIMG_OK;
