@@ -156,8 +156,8 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().b200timg_ctx_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.b200timg_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -297,78 +297,133 @@ __device__ __forceinline__ int fs_tap(int v, int e, int k) {      // error_diffu
     const int q = (t + ((t >> 31) & 15)) >> 4;                  // C division truncates toward zero
     return min(255, max(0, v + q));
 }
-constexpr int DW = 16;                                            // warps per frame CTA
+constexpr int DW_MAX = 32;     // warps per frame CTA (upper bound; the launch picks how many)
+constexpr int DCH = 16;        // columns per staged chunk
+constexpr int DIN_STRIDE = DCH + 1;              // u32 words per staged row (odd: lanes hit distinct banks)
+constexpr int DOUT_STRIDE = 20;                  // bytes per staged output row (5 words: conflict-free)
+constexpr int DWARP_SMEM = 2 * 32 * DIN_STRIDE * 4 + 32 * DOUT_STRIDE;   // per warp
 
-__global__ void __launch_bounds__(DW * 32)
-sixel_dither_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W) {
-    extern __shared__ uint8_t s_lut[];                            // 32768
+// A warp owns a band of 32 rows; lane l runs row band*32+l two columns behind lane l-1, so the three
+// errors it needs from the row above arrive by one shuffle per step.  Pixels are staged through
+// shared memory in chunks of DCH steps, pre-skewed (row r of the tile starts at column base-2r) and
+// loaded/stored by half-warps so global traffic is 64-byte segments instead of 32 scattered lines.
+// Consecutive bands are pipelined through a boundary row of packed errors in global memory (L2)
+// plus a per-band progress counter in shared memory.
+__global__ void __launch_bounds__(DW_MAX * 32)
+sixel_dither_kernel(const uint32_t *__restrict__ fb, int w, int h, int nwarps, SixelWork W) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];              // lut[32768] | per-warp tiles
     __shared__ uint32_t s_pal[256];
     __shared__ volatile int s_progress[2048];                     // columns completed by each band's last row
     const int f = blockIdx.x;
     const SixelFrameHdr *hdr = W.hdr + f;
     if (!hdr->diffuse) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < 32768 / 4; i += DW * 32)
+    const int nthreads = nwarps * 32;
+    uint8_t *s_lut = s_dyn;
+    for (int i = tid; i < 32768 / 4; i += nthreads)
         reinterpret_cast<uint32_t *>(s_lut)[i] = reinterpret_cast<const uint32_t *>(W.lut + (long long)f * 32768)[i];
-    if (tid < 256) s_pal[tid] = hdr->palette[tid];
-    for (int i = tid; i < W.nb32; i += DW * 32) s_progress[i] = 0;
+    for (int i = tid; i < 256; i += nthreads) s_pal[i] = hdr->palette[i];     // nthreads may be < 256
+    for (int i = tid; i < W.nb32; i += nthreads) s_progress[i] = 0;
     __syncthreads();
+    uint32_t *s_in = reinterpret_cast<uint32_t *>(s_dyn + 32768 + (size_t)wid * DWARP_SMEM);   // [2][32][DIN_STRIDE]
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_in + 2 * 32 * DIN_STRIDE);                    // [32][DOUT_STRIDE]
     const uint32_t *frame = fb + (long long)f * w * h;
     uint8_t *index = W.index + (long long)f * w * h;
     uint32_t *bnd = W.boundary + (long long)f * W.nb32 * w;
+    const int hrow = lane >> 4, hcol = lane & 15;                 // half-warp staging coordinates
 
-    for (int band = wid; band < W.nb32; band += DW) {
+    for (int band = wid; band < W.nb32; band += nwarps) {
         const int y = band * 32 + lane;
         const bool row_ok = y < h;
-        const uint32_t *rowp = frame + (long long)(row_ok ? y : 0) * w;
-        uint8_t *outp = index + (long long)(row_ok ? y : 0) * w;
+        const bool last_row = (y == h - 1);
         const uint32_t *bin = band > 0 ? bnd + (long long)(band - 1) * w : nullptr;
         uint32_t *bout = bnd + (long long)band * w;
-        const bool last_row = (y == h - 1);
         uint32_t last_e = EZ, up_m1 = EZ, up_0 = EZ, up_p1 = EZ, own = EZ, e_first = EZ;
-        const int steps = w + 62;
-        for (int t = 0; t < steps; ++t) {
-            if (band > 0 && (t & 31) == 0) {                      // stay behind the previous band's last row
-                const int need = min(w, t + 33);
-                if (lane == 0) while (s_progress[band - 1] < need) __nanosleep(64);
-                __syncwarp();
-            }
-            const int x = t - 2 * lane;
-            if (t == 0 && lane == 0 && bin) up_p1 = __ldcg(bin);   // e(0, y-1): lane 0 has no warm-up step
-            uint32_t recv = __shfl_up_sync(0xffffffffu, last_e, 1);
-            if (lane == 0) recv = (bin && x + 1 < w) ? __ldcg(bin + x + 1) : EZ;
-            up_m1 = up_0; up_0 = up_p1; up_p1 = recv;
-            if (x >= 0 && x < w && row_ok) {
-                const uint32_t px = rowp[x];
-                int v[3] = {(int)(px & 0xff), (int)((px >> 8) & 0xff), (int)((px >> 16) & 0xff)};
+        const int steps = w + 62, nchunks = (steps + DCH - 1) / DCH;
+        // pre-skewed load of chunk c into registers: element i covers tile row 2i+hrow, column hcol
+        uint32_t pre[16];
+        auto load_chunk = [&](int c) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const int sh = 9 * c;
-                    v[c] = fs_tap(v[c], (int)((up_m1 >> sh) & 511) - 256, 1);      // from (x-1, y-1)
-                    v[c] = fs_tap(v[c], (int)((up_0 >> sh) & 511) - 256, 5);       // from (x,   y-1)
-                    v[c] = fs_tap(v[c], (int)((up_p1 >> sh) & 511) - 256, 3);      // from (x+1, y-1)
-                    if (x == w - 1) v[c] = fs_tap(v[c], (int)((e_first >> sh) & 511) - 256, 3);   // libsixel: (0,y)'s below-left tap
-                    v[c] = fs_tap(v[c], (int)((own >> sh) & 511) - 256, 7);        // from (x-1, y)
-                }
-                const uint32_t cell = ((uint32_t)(v[0] >> 3) << 10) | ((uint32_t)(v[1] >> 3) << 5) | (uint32_t)(v[2] >> 3);
-                const uint32_t ci = s_lut[cell];
-                const uint32_t pal = s_pal[ci];
-                uint32_t e = EZ;
-                if (x < w - 1 && !last_row)
-                    e = (uint32_t)(v[0] - (int)(pal & 0xff) + 256) | ((uint32_t)(v[1] - (int)((pal >> 8) & 0xff) + 256) << 9)
-                      | ((uint32_t)(v[2] - (int)((pal >> 16) & 0xff) + 256) << 18);
-                if (x == 0) e_first = e;
-                own = e; last_e = e;
-                outp[x] = (uint8_t)ci;
-                if (lane == 31) {
-                    __stcg(bout + x, e);
-                    if ((x & 31) == 31 || x == w - 1) { __threadfence_block(); s_progress[band] = x + 1; }
-                }
-            } else if (x >= w) {
-                last_e = EZ;
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + hrow, yy = band * 32 + r, x = c * DCH - 2 * r + hcol;
+                pre[i] = (yy < h && x >= 0 && x < w) ? frame[(long long)yy * w + x] : 0u;
             }
+        };
+        auto store_chunk = [&](int c) {
+            uint32_t *t = s_in + (c & 1) * 32 * DIN_STRIDE;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[(2 * i + hrow) * DIN_STRIDE + hcol] = pre[i];
+        };
+        load_chunk(0); store_chunk(0);
+        __syncwarp();
+        for (int c = 0; c < nchunks; ++c) {
+            const int t0 = c * DCH;
+            if (c + 1 < nchunks) load_chunk(c + 1);                // in flight while this chunk computes
+            uint32_t binreg = EZ;
+            if (band > 0) {                                       // stay behind the previous band's last row
+                const int need = min(w, t0 + DCH + 1);
+                if (lane == 0) { while (s_progress[band - 1] < need) __nanosleep(32); __threadfence_block(); }
+                __syncwarp();
+                const int bx = t0 + 1 + lane;                     // lane 0 consumes bin[t+1] at step t
+                if (lane < DCH && bx < w) binreg = __ldcg(bin + bx);
+                if (c == 0 && lane == 0) up_p1 = __ldcg(bin);     // e(0, y-1): lane 0 has no warm-up step
+            }
+            const uint32_t *tin = s_in + (c & 1) * 32 * DIN_STRIDE + lane * DIN_STRIDE;
+            uint32_t bkeep = EZ;
+#pragma unroll 4
+            for (int j = 0; j < DCH; ++j) {
+                const int t = t0 + j, x = t - 2 * lane;
+                uint32_t recv = __shfl_up_sync(0xffffffffu, last_e, 1);
+                const uint32_t b0 = __shfl_sync(0xffffffffu, binreg, j);
+                if (lane == 0) recv = b0;
+                up_m1 = up_0; up_0 = up_p1; up_p1 = recv;
+                uint32_t ci = 0;
+                if (x >= 0 && x < w && row_ok) {
+                    const uint32_t px = tin[j];
+                    int v[3] = {(int)(px & 0xff), (int)((px >> 8) & 0xff), (int)((px >> 16) & 0xff)};
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const int sh = 9 * ch;
+                        v[ch] = fs_tap(v[ch], (int)((up_m1 >> sh) & 511) - 256, 1);      // from (x-1, y-1)
+                        v[ch] = fs_tap(v[ch], (int)((up_0 >> sh) & 511) - 256, 5);       // from (x,   y-1)
+                        v[ch] = fs_tap(v[ch], (int)((up_p1 >> sh) & 511) - 256, 3);      // from (x+1, y-1)
+                        if (x == w - 1) v[ch] = fs_tap(v[ch], (int)((e_first >> sh) & 511) - 256, 3);   // libsixel: (0,y)'s below-left tap
+                        v[ch] = fs_tap(v[ch], (int)((own >> sh) & 511) - 256, 7);        // from (x-1, y)
+                    }
+                    const uint32_t cell = ((uint32_t)(v[0] >> 3) << 10) | ((uint32_t)(v[1] >> 3) << 5) | (uint32_t)(v[2] >> 3);
+                    ci = s_lut[cell];
+                    const uint32_t pal = s_pal[ci];
+                    uint32_t e = EZ;
+                    if (x < w - 1 && !last_row)
+                        e = (uint32_t)(v[0] - (int)(pal & 0xff) + 256) | ((uint32_t)(v[1] - (int)((pal >> 8) & 0xff) + 256) << 9)
+                          | ((uint32_t)(v[2] - (int)((pal >> 16) & 0xff) + 256) << 18);
+                    if (x == 0) e_first = e;
+                    own = e; last_e = e;
+                } else if (x >= w) {
+                    last_e = EZ;
+                }
+                s_out[lane * DOUT_STRIDE + j] = (uint8_t)ci;
+                const uint32_t e31 = __shfl_sync(0xffffffffu, last_e, 31);      // the band's last row, column t-62
+                if (lane == j) bkeep = e31;
+            }
+            __syncwarp();
+            // write this chunk's indices: half-warp per row, 16 contiguous bytes
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + hrow, yy = band * 32 + r, x = t0 - 2 * r + hcol;
+                if (yy < h && x >= 0 && x < w) index[(long long)yy * w + x] = s_out[r * DOUT_STRIDE + hcol];
+            }
+            {   // boundary row for the next band, then publish progress
+                const int x = t0 + lane - 62;
+                if (lane < DCH && x >= 0 && x < w) __stcg(bout + x, bkeep);
+                __threadfence_block();                            // every storing lane orders its own store ...
+                __syncwarp();                                     // ... before lane 0 raises the flag
+                const int done = min(w, t0 + DCH - 62);
+                if (lane == 0 && done > 0) s_progress[band] = done;
+            }
+            if (c + 1 < nchunks) store_chunk(c + 1);
+            __syncwarp();
         }
-        if (lane == 31 && !row_ok) { __threadfence_block(); s_progress[band] = w; }   // ragged last band: nobody waits, but be tidy
     }
 }
 
@@ -681,7 +736,15 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
         B2_LAUNCH_CHECK(ctx);
     }
     B2_KERNEL(ctx, "sixel_dither_kernel");
-    sixel_dither_kernel<<<n_frames, DW * 32, 32768, ctx->stream>>>(fb, w, h, W);
+    {
+        // warps per frame: as many as fit, but in full rounds over the 32-row bands
+        const int rounds = (W.nb32 + DW_MAX - 1) / DW_MAX;
+        const int nwarps = (W.nb32 + rounds - 1) / rounds;
+        const size_t dsmem = 32768 + (size_t)nwarps * DWARP_SMEM;
+        static bool dattr = false;
+        if (!dattr) { B2_CUDA(ctx, cudaFuncSetAttribute(sixel_dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + DW_MAX * DWARP_SMEM)); dattr = true; }
+        sixel_dither_kernel<<<n_frames, nwarps * 32, dsmem, ctx->stream>>>(fb, w, h, nwarps, W);
+    }
     B2_LAUNCH_CHECK(ctx);
     B2_KERNEL(ctx, "sixel_emit_kernel");
     sixel_emit_kernel<false><<<egrid, ET, emit_smem, ctx->stream>>>(G, W, nullptr, nullptr, 0);
