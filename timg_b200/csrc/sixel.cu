@@ -497,6 +497,7 @@ sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets,
                   unsigned long long out_cap) {
     extern __shared__ uint32_t s_sorted[];                   // [6*w]
     __shared__ unsigned short s_cnt[EW][256];
+    __shared__ uint32_t s_mask[EW * 256];
     __shared__ uint32_t s_w[ET / 32];
     __shared__ uint32_t s_colbase[256];
     const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -510,7 +511,7 @@ sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets,
         if (fbase + hdr->frame_size > out_cap) return;       // never write out of bounds
         band_off = W.band_bytes[(long long)f * W.nbands + band];
     }
-    for (int i = tid; i < EW * 256; i += ET) (&s_cnt[0][0])[i] = 0;
+    for (int i = tid; i < EW * 256; i += ET) { (&s_cnt[0][0])[i] = 0; s_mask[i] = 0; }
     __syncthreads();
 
     if (WRITE && band == 0) {                                // header: DCS q, raster attributes, palette
@@ -566,7 +567,10 @@ sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets,
         for (int k = 0; k < EW; ++k) { const uint32_t v = s_cnt[k][tid]; s_cnt[k][tid] = (unsigned short)run; run += v; }
     }
     __syncthreads();
-    // (1b) scatter
+    // (1b) scatter.  Ranks must follow x; inside one 32-column step a colour can sit in different
+    // slots of different columns, so the lanes holding each colour are first collected in a per-warp
+    // mask table and the rank is the number of lower lanes in that mask.
+    uint32_t *M = s_mask + wid * 256;
     for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
         const int x = x0 + lane;
         uint32_t col[6], bits[6];
@@ -577,28 +581,22 @@ sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets,
             const uint32_t vm = __ballot_sync(0xffffffffu, have);
             if (have) {
                 const uint32_t m = __match_any_sync(vm, col[s]);
-                const uint32_t below = __popc(m & ((1u << lane) - 1));
-                const uint32_t at = s_cnt[wid][col[s]];
-                s_sorted[at + below] = ent_pack(col[s], (uint32_t)x, bits[s]);
-                __syncwarp(vm);
-                if (below == 0) s_cnt[wid][col[s]] = (unsigned short)(at + __popc(m));
+                if ((m & ((1u << lane) - 1)) == 0) M[col[s]] |= m;
             }
             __syncwarp();
         }
-    }
-    __syncthreads();
-    // Inside one 32-column step a colour may sit in different slots of different columns, so a
-    // (warp, colour) segment is ordered by (step, slot, lane) rather than by x: sort each of the
-    // EW*256 tiny segments (packed words compare as (colour, x)).
-    for (int seg = tid; seg < EW * 256; seg += ET) {
-        const int c = seg & 255, k = seg >> 8;
-        const int beg = k > 0 ? s_cnt[k - 1][c] : (int)s_colbase[c], end = s_cnt[k][c];
-        for (int i = beg + 1; i < end; ++i) {
-            const uint32_t v = s_sorted[i];
-            int j = i - 1;
-            while (j >= beg && s_sorted[j] > v) { s_sorted[j + 1] = s_sorted[j]; --j; }
-            s_sorted[j + 1] = v;
-        }
+        uint32_t mk[6];
+#pragma unroll
+        for (int s = 0; s < 6; ++s)
+            if (s < ns) {
+                mk[s] = M[col[s]];
+                s_sorted[s_cnt[wid][col[s]] + __popc(mk[s] & ((1u << lane) - 1))] = ent_pack(col[s], (uint32_t)x, bits[s]);
+            }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 6; ++s)
+            if (s < ns && (mk[s] & ((1u << lane) - 1)) == 0) { s_cnt[wid][col[s]] += (unsigned short)__popc(mk[s]); M[col[s]] = 0; }
+        __syncwarp();
     }
     __syncthreads();
     // (2) sizes
@@ -712,7 +710,7 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
 
     static bool attrs_set = false;
     EmitGeom G; G.w = w; G.h = h; G.cols_per_warp = ((w + EW - 1) / EW + 31) / 32 * 32;
-    const size_t smem_limit = 227 * 1024 - 16 * 1024;
+    const size_t smem_limit = 227 * 1024 - 30 * 1024;   // the emit kernel also has ~26 KB of static shared memory
     const size_t emit_smem = sizeof(uint32_t) * (size_t)6 * w;
     if (w > 4095 || emit_smem > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
     if (!attrs_set) {
