@@ -42,7 +42,10 @@ struct SixelWork {                     // device pointers into ctx->sixel_work
     uint8_t *lut;                      // [n_frames][32768]
     uint8_t *index;                    // [n_frames][w*h]
     uint32_t *boundary;                // [n_frames][nb32][w] packed errors of each 32-row band's last row
-    uint32_t *band_bytes;              // [n_frames][nbands]  (sizes, then exclusive offsets in place)
+    uint32_t *band_bytes;              // [n_frames][nbands]  sizes
+    uint32_t *band_off;                // [n_frames][nbands]  offset of each band's first byte inside its frame
+    char *scratch;                     // [n_frames][nbands][band_cap] band bytes before compaction
+    size_t band_cap;
     int ent_cap, nb32, nbands;
 };
 
@@ -491,10 +494,8 @@ __device__ __forceinline__ RunInfo run_info(const uint32_t *sorted, int i, int n
 // One CTA per 6-row band.  (1) per-warp counting sort of the band's (colour, x, bits) entries by
 // colour -- warps own contiguous column ranges, so warp-major order is x order and the sort is
 // stable; (2) every run head sizes its "gap + run" bytes, block scan -> offsets; (3) WRITE: bytes.
-template <bool WRITE>
 __global__ void __launch_bounds__(ET)
-sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets, char *__restrict__ out,
-                  unsigned long long out_cap) {
+sixel_emit_kernel(EmitGeom G, SixelWork W) {
     extern __shared__ uint32_t s_sorted[];                   // [6*w]
     __shared__ unsigned short s_cnt[EW][256];
     __shared__ uint32_t s_mask[EW * 256];
@@ -505,39 +506,8 @@ sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets,
     const SixelFrameHdr *hdr = W.hdr + f;
     const uint8_t *idx = W.index + ((long long)f * G.h + (long long)band * 6) * w;
 
-    unsigned long long fbase = 0; uint32_t band_off = 0;
-    if (WRITE) {
-        fbase = offsets[f];
-        if (fbase + hdr->frame_size > out_cap) return;       // never write out of bounds
-        band_off = W.band_bytes[(long long)f * W.nbands + band];
-    }
     for (int i = tid; i < EW * 256; i += ET) { (&s_cnt[0][0])[i] = 0; s_mask[i] = 0; }
     __syncthreads();
-
-    if (WRITE && band == 0) {                                // header: DCS q, raster attributes, palette
-        if (tid == 0) {
-            char *o = out + fbase;
-            *o++ = '\033'; *o++ = 'P'; *o++ = 'q'; *o++ = '"'; *o++ = '1'; *o++ = ';'; *o++ = '1'; *o++ = ';';
-            o = put_num_u(o, (uint32_t)w); *o++ = ';'; o = put_num_u(o, (uint32_t)G.h);
-        }
-        const uint32_t fixed = 8 + ndig_u((uint32_t)w) + 1 + ndig_u((uint32_t)G.h);
-        uint32_t len = 0, r = 0, g = 0, b = 0;
-        if ((uint32_t)tid < hdr->ncolors) {                  // output_rgb_palette_definition: (v*100+127)/255 percent
-            const uint32_t p = hdr->palette[tid];
-            r = ((p & 0xff) * 100 + 127) / 255; g = (((p >> 8) & 0xff) * 100 + 127) / 255; b = (((p >> 16) & 0xff) * 100 + 127) / 255;
-            len = 1 + ndig_u((uint32_t)tid) + 3 + ndig_u(r) + 1 + ndig_u(g) + 1 + ndig_u(b);
-        }
-        uint32_t tot; const uint32_t at = block_excl_scan<ET>(len, s_w, tot);
-        if (len) {
-            char *q = out + fbase + fixed + at;
-            *q++ = '#'; q = put_num_u(q, (uint32_t)tid); *q++ = ';'; *q++ = '2'; *q++ = ';';
-            q = put_num_u(q, r); *q++ = ';'; q = put_num_u(q, g); *q++ = ';'; q = put_num_u(q, b);
-        }
-    }
-    if (WRITE && tid == 0) {
-        if (band > 0) out[fbase + band_off - 1] = '-';       // DECGNL between bands
-        if (band == W.nbands - 1) { out[fbase + hdr->frame_size - 2] = '\033'; out[fbase + hdr->frame_size - 1] = '\\'; }
-    }
 
     // (1a) count entries per (warp, colour)
     const int x_lo = wid * G.cols_per_warp, x_hi = min(w, x_lo + G.cols_per_warp);
@@ -606,9 +576,9 @@ sixel_emit_kernel(EmitGeom G, SixelWork W, const uint64_t *__restrict__ offsets,
     uint32_t local = 0;
     for (int i = lo; i < hi; ++i) local += run_info(s_sorted, i, n, minc).bytes;
     uint32_t band_total; uint32_t at = block_excl_scan<ET>(local, s_w, band_total);
-    if (!WRITE) { if (tid == 0) W.band_bytes[(long long)f * W.nbands + band] = band_total; return; }
-    // (3) bytes
-    char *o = out + fbase + band_off + at;
+    if (tid == 0) W.band_bytes[(long long)f * W.nbands + band] = band_total;
+    // (3) bytes, into this band's scratch slot (compacted into the final stream later)
+    char *o = W.scratch + ((size_t)f * W.nbands + band) * W.band_cap + at;
     for (int i = lo; i < hi; ++i) {
         const RunInfo r = run_info(s_sorted, i, n, minc);
         if (!r.bytes) continue;
@@ -640,7 +610,7 @@ sixel_layout_kernel(int w, int h, SixelWork W) {
         const int b = b0 + tid;
         const uint32_t v = b < W.nbands ? bb[b] + (b > 0 ? 1u : 0u) : 0;       // '-' before every band but the first
         uint32_t tot; const uint32_t at = block_excl_scan<256>(v, s_w, tot);
-        if (b < W.nbands) bb[b] = s_carry + at + (b > 0 ? 1u : 0u);            // offset of the band's first data byte
+        if (b < W.nbands) W.band_off[(long long)f * W.nbands + b] = s_carry + at + (b > 0 ? 1u : 0u);   // band's first data byte
         __syncthreads();
         if (tid == 0) s_carry += tot;
         __syncthreads();
@@ -673,6 +643,47 @@ sixel_sizes_to_offsets_kernel(const SixelFrameHdr *__restrict__ hdr, int n, uint
     if (tid == 0) offsets[n] = c_run;
 }
 
+// Final assembly: header + palette (band 0's CTA), every band's bytes copied from its scratch slot
+// to its place in the compacted stream, '-' between bands, ST at the end.  Pure byte traffic.
+__global__ void __launch_bounds__(256)
+sixel_compact_kernel(int w, int h, SixelWork W, const uint64_t *__restrict__ offsets, char *__restrict__ out,
+                     unsigned long long out_cap) {
+    __shared__ uint32_t s_w[8];
+    const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const SixelFrameHdr *hdr = W.hdr + f;
+    const unsigned long long fbase = offsets[f];
+    if (fbase + hdr->frame_size > out_cap) return;           // never write out of bounds
+    const uint32_t boff = W.band_off[(long long)f * W.nbands + band];
+    const uint32_t n = W.band_bytes[(long long)f * W.nbands + band];
+    const char *src = W.scratch + ((size_t)f * W.nbands + band) * W.band_cap;
+    char *dst = out + fbase + boff;
+    for (uint32_t i = tid; i < n; i += 256) dst[i] = src[i];
+    if (tid == 0) {
+        if (band > 0) dst[-1] = '-';                         // DECGNL between bands
+        if (band == W.nbands - 1) { out[fbase + hdr->frame_size - 2] = '\033'; out[fbase + hdr->frame_size - 1] = '\\'; }
+    }
+    if (band == 0) {                                         // DCS q, raster attributes, palette definitions
+        if (tid == 0) {
+            char *o = out + fbase;
+            *o++ = '\033'; *o++ = 'P'; *o++ = 'q'; *o++ = '"'; *o++ = '1'; *o++ = ';'; *o++ = '1'; *o++ = ';';
+            o = put_num_u(o, (uint32_t)w); *o++ = ';'; o = put_num_u(o, (uint32_t)h);
+        }
+        const uint32_t fixed = 8 + ndig_u((uint32_t)w) + 1 + ndig_u((uint32_t)h);
+        uint32_t len = 0, r = 0, g = 0, b = 0;
+        if ((uint32_t)tid < hdr->ncolors) {                  // output_rgb_palette_definition: (v*100+127)/255 percent
+            const uint32_t p = hdr->palette[tid];
+            r = ((p & 0xff) * 100 + 127) / 255; g = (((p >> 8) & 0xff) * 100 + 127) / 255; b = (((p >> 16) & 0xff) * 100 + 127) / 255;
+            len = 1 + ndig_u((uint32_t)tid) + 3 + ndig_u(r) + 1 + ndig_u(g) + 1 + ndig_u(b);
+        }
+        uint32_t tot; const uint32_t at = block_excl_scan<256>(len, s_w, tot);
+        if (len) {
+            char *q = out + fbase + fixed + at;
+            *q++ = '#'; q = put_num_u(q, (uint32_t)tid); *q++ = ';'; *q++ = '2'; *q++ = ';';
+            q = put_num_u(q, r); *q++ = ';'; q = put_num_u(q, g); *q++ = ';'; q = put_num_u(q, b);
+        }
+    }
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // phases: 1 = everything up to and including the frame offsets (sizes known, nothing written),
@@ -698,6 +709,10 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     const size_t o_idx = off; off += align_up((size_t)npix * n_frames, 256);
     const size_t o_bnd = off; off += align_up(sizeof(uint32_t) * (size_t)W.nb32 * w * n_frames, 256);
     const size_t o_bb = off; off += align_up(sizeof(uint32_t) * (size_t)W.nbands * n_frames, 256);
+    const size_t o_bo = off; off += align_up(sizeof(uint32_t) * (size_t)W.nbands * n_frames, 256);
+    // worst case of one band: <= 6 entries per column, <= 7 bytes each ("!nnnn?" + char), "$#ccc" per colour
+    W.band_cap = align_up((size_t)w * 42 + 256 * 5 + 16, 256);
+    const size_t o_scr = off; off += W.band_cap * W.nbands * n_frames;
     if (phases & 1) B2_CUDA(ctx, ctx->sixel_work.reserve(off));
     if (!ctx->sixel_work.p || ctx->sixel_work.cap < off) return ctx->fail(B200TIMG_EINVAL, "sixel: write phase without prepare");
     ctx->sixel_idx_off = o_idx;
@@ -706,6 +721,7 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     W.ent_a = reinterpret_cast<uint32_t *>(base + o_ea); W.ent_b = reinterpret_cast<uint32_t *>(base + o_eb);
     W.lut = reinterpret_cast<uint8_t *>(base + o_lut); W.index = reinterpret_cast<uint8_t *>(base + o_idx);
     W.boundary = reinterpret_cast<uint32_t *>(base + o_bnd); W.band_bytes = reinterpret_cast<uint32_t *>(base + o_bb);
+    W.band_off = reinterpret_cast<uint32_t *>(base + o_bo); W.scratch = base + o_scr;
     const uint32_t *fb = reinterpret_cast<const uint32_t *>(d_fb);
 
     static bool attrs_set = false;
@@ -715,8 +731,7 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     if (w > 4095 || emit_smem > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
     if (!attrs_set) {
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
         attrs_set = true;
     }
     const dim3 egrid(W.nbands, n_frames);
@@ -745,7 +760,7 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     }
     B2_LAUNCH_CHECK(ctx);
     B2_KERNEL(ctx, "sixel_emit_kernel");
-    sixel_emit_kernel<false><<<egrid, ET, emit_smem, ctx->stream>>>(G, W, nullptr, nullptr, 0);
+    sixel_emit_kernel<<<egrid, ET, emit_smem, ctx->stream>>>(G, W);
     B2_LAUNCH_CHECK(ctx);
     B2_KERNEL(ctx, "sixel_layout_kernel");
     sixel_layout_kernel<<<n_frames, 256, 0, ctx->stream>>>(w, h, W);
@@ -755,8 +770,8 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     B2_LAUNCH_CHECK(ctx);
     }
     if (!(phases & 2)) return B200TIMG_OK;
-    B2_KERNEL(ctx, "sixel_emit_kernel");
-    sixel_emit_kernel<true><<<egrid, ET, emit_smem, ctx->stream>>>(G, W, d_offsets, d_out, (unsigned long long)out_cap);
+    B2_KERNEL(ctx, "sixel_compact_kernel");
+    sixel_compact_kernel<<<egrid, 256, 0, ctx->stream>>>(w, h, W, d_offsets, d_out, (unsigned long long)out_cap);
     B2_LAUNCH_CHECK(ctx);
     return B200TIMG_OK;
 }
