@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true", help="print just the per-kernel table (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -328,7 +329,10 @@ def main():
         except Exception as ex:            # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": f"failed: {ex}"}
 
-    if rank == 0:
+    if rank == 0 and args.kernels_only:
+        print(f"value {value:.0f} Mpx/s  ms/step {ms_total / args.steps:.3f}  " +
+              "  ".join(f"{k.replace('sixel_', '').replace('_kernel', '')}={v['ms_per_launch']:.3f}" for k, v in kernels.items()))
+    elif rank == 0:
         line = {"metric": "Mpixels/s scale+dither+sixel-encode @4K->cell", "value": value, "unit": "Mpx/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",

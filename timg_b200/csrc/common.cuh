@@ -55,6 +55,7 @@ struct b200timg_ctx {
     int device = 0;
     b200timg::ResamplePlan *plan = nullptr;   // cached resampling tables (host copy) ...
     int plan_key[4] = {0, 0, 0, 0};           // ... for this iw, ih, ow, oh (device copy in `tables`)
+    long long fixed_geom_key = -1;            // which tile-origin arrays are uploaded behind ctx->misc + 4096
     size_t sixel_idx_off = 0;                 // where the last sixel encode put its index planes
     cudaStream_t stream = nullptr;
     bool own_stream = false;

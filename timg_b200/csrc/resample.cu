@@ -9,6 +9,8 @@
 // v1 layout: one thread per output pixel, taps read straight from global memory (the
 // working set of a tile stays in L1/L2).  Algorithmic bytes: 4*iw*ih read + 4*ow*oh written.
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "resample_tables.h"
@@ -296,6 +298,175 @@ resample_tiled_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
     }
 }
 
+// ---- fixed-tap fast path ------------------------------------------------------------------
+// Same algorithm as resample_tiled_kernel, specialised so the inner loops carry no predicates and
+// no run-time trip counts: every output uses exactly HC horizontal and VC vertical taps (the
+// per-axis widest count rounded up to 2/4/6/8); taps an output does not have are zero coefficients
+// reading staged (finite) pixels, which adds +0 and changes nothing.  The staged window is padded
+// accordingly (zeros outside the image), its origin per tile column/row comes from the host.
+struct FixedGeom { int nix, niy; const int32_t *tile_ix0, *tile_iy0; };
+constexpr int FTW = 64, FTH = 16;
+
+template <bool VFIRST, int HC, int VC>
+__global__ void __launch_bounds__(RT, 3)
+resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, FixedGeom G) {
+    extern __shared__ float4 s_px[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.z;
+    const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * FTH;
+    const int ix0 = G.tile_ix0[blockIdx.x], iy0 = G.tile_iy0[blockIdx.y];
+    const int nix = G.nix, niy = G.niy;
+    float4 *Din = s_px;
+    float4 *T = s_px + (size_t)niy * nix;
+    int *s_hfirst = reinterpret_cast<int *>(T + (VFIRST ? FTH * nix : niy * FTW));   // [FTW]
+    int *s_vfirst = s_hfirst + FTW;                                                   // [FTH]
+    float *s_hc = reinterpret_cast<float *>(s_vfirst + FTH);                          // [FTW][HC+1]
+    float *s_vc = s_hc + FTW * (HC + 1);                                              // [FTH][VC+1]
+    if (tid < FTW) {
+        const int ox = ox0 + tid;
+        const bool ok = ox < P.ow;
+        s_hfirst[tid] = ok ? P.h_first[ox] - ix0 : 0;
+#pragma unroll
+        for (int i = 0; i < HC; ++i) s_hc[tid * (HC + 1) + i] = (ok && i < P.h_widest) ? P.h_coeff[(long long)ox * P.h_widest + i] : 0.0f;
+    } else if (tid < FTW + FTH) {
+        const int t = tid - FTW, oy = oy0 + t;
+        const bool ok = oy < P.oh;
+        s_vfirst[t] = ok ? P.v_first[oy] - iy0 : 0;
+#pragma unroll
+        for (int i = 0; i < VC; ++i) s_vc[t * (VC + 1) + i] = (ok && i < P.v_widest) ? P.v_coeff[(long long)oy * P.v_widest + i] : 0.0f;
+    }
+    const uint32_t *src = in + (long long)f * P.iw * P.ih;
+    const bool hseq = P.h_sequential != 0;
+    const float tiny = 7.5231638452626401e-37f;       // 2^-120
+    const int tx = tid & (FTW - 1), tyb = tid >> 6;   // this thread's pixels: column tx, rows tyb + 4q
+
+    float4 res[4], plain[4];
+    bool need_plain = false;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int ly = wid; ly < niy; ly += RT / 32) {
+            const int y = iy0 + ly;
+            const uint32_t *row = src + (long long)y * P.iw;
+            float4 *drow = Din + ly * nix;
+            for (int lx = lane; lx < nix; lx += 32) {
+                const int x = ix0 + lx;
+                const uint32_t p = (y < P.ih && x < P.iw) ? row[x] : 0u;
+                drow[lx] = pass == 0 ? decode_pm(p, P.bgra) : decode_plain(p, P.bgra);
+            }
+        }
+        __syncthreads();
+        float4 acc[4];
+        if (VFIRST) {
+#pragma unroll
+            for (int r = 0; r < FTH / (RT / 32); ++r) {
+                const int ty = wid + r * (RT / 32);
+                float vc[VC];
+#pragma unroll
+                for (int k = 0; k < VC; ++k) vc[k] = s_vc[ty * (VC + 1) + k];
+                const float4 *base = Din + s_vfirst[ty] * nix;
+                float4 *trow = T + ty * nix;
+                for (int lx = lane; lx < nix; lx += 32) {
+                    const float4 *col = base + lx;
+                    float4 a = mul4(col[0], vc[0]);
+#pragma unroll
+                    for (int k = 1; k < VC; ++k) a = add4(a, mul4(col[k * nix], vc[k]));
+                    trow[lx] = a;
+                }
+            }
+            __syncthreads();
+            float hc[HC];
+#pragma unroll
+            for (int i = 0; i < HC; ++i) hc[i] = s_hc[tx * (HC + 1) + i];
+            const float4 *tbase = T + s_hfirst[tx];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 *row = tbase + (tyb + 4 * q) * nix;
+                if (hseq) {
+                    float4 a = mul4(row[0], hc[0]);
+#pragma unroll
+                    for (int i = 1; i < (HC < 3 ? HC : 3); ++i) a = add4(a, mul4(row[i], hc[i]));
+                    acc[q] = a;
+                } else {
+                    float4 a0 = mul4(row[0], hc[0]), a1 = mul4(row[1], hc[1]);
+#pragma unroll
+                    for (int i = 2; i < HC; ++i) { if (i & 1) a1 = add4(a1, mul4(row[i], hc[i])); else a0 = add4(a0, mul4(row[i], hc[i])); }
+                    acc[q] = add4(a0, a1);
+                }
+            }
+        } else {
+            float hc[HC];
+#pragma unroll
+            for (int i = 0; i < HC; ++i) hc[i] = s_hc[tx * (HC + 1) + i];
+            const int hn0 = s_hfirst[tx];
+            for (int ly = tyb; ly < niy; ly += 4) {
+                const float4 *row = Din + ly * nix + hn0;
+                float4 r;
+                if (hseq) {
+                    r = mul4(row[0], hc[0]);
+#pragma unroll
+                    for (int i = 1; i < (HC < 3 ? HC : 3); ++i) r = add4(r, mul4(row[i], hc[i]));
+                } else {
+                    float4 a0 = mul4(row[0], hc[0]), a1 = mul4(row[1], hc[1]);
+#pragma unroll
+                    for (int i = 2; i < HC; ++i) { if (i & 1) a1 = add4(a1, mul4(row[i], hc[i])); else a0 = add4(a0, mul4(row[i], hc[i])); }
+                    r = add4(a0, a1);
+                }
+                T[ly * FTW + tx] = r;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ty = tyb + 4 * q;
+                const float4 *col = T + s_vfirst[ty] * FTW + tx;
+                const float *vc = s_vc + ty * (VC + 1);
+                float4 a = mul4(col[0], vc[0]);
+#pragma unroll
+                for (int k = 1; k < VC; ++k) a = add4(a, mul4(col[k * FTW], vc[k]));
+                acc[q] = a;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { if (pass == 0) res[q] = acc[q]; else plain[q] = acc[q]; }
+        if (pass == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (ox0 + tx < P.ow && oy0 + tyb + 4 * q < P.oh && res[q].w < tiny) need_plain = true;
+            if (!__syncthreads_or(need_plain)) break;
+        }
+    }
+    if (ox0 + tx < P.ow) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int oy = oy0 + tyb + 4 * q;
+            if (oy < P.oh) {
+                float v[7];
+                v[3] = res[q].w; v[4] = res[q].x; v[5] = res[q].y; v[6] = res[q].z;
+                const bool transparent = res[q].w < tiny;
+                v[0] = transparent ? plain[q].x : 0.f; v[1] = transparent ? plain[q].y : 0.f; v[2] = transparent ? plain[q].z : 0.f;
+                out[((long long)f * P.out_frame_rows + oy) * P.ow + ox0 + tx] = encode_px(v);
+            }
+        }
+    }
+}
+
+typedef void (*FixedFn)(const uint32_t *, uint32_t *, ResampleParams, FixedGeom);
+template <bool VF, int HC>
+static FixedFn fixed_v(int vc) {
+    switch (vc) {
+    case 2: return resample_fixed_kernel<VF, HC, 2>;
+    case 4: return resample_fixed_kernel<VF, HC, 4>;
+    case 6: return resample_fixed_kernel<VF, HC, 6>;
+    default: return resample_fixed_kernel<VF, HC, 8>;
+    }
+}
+template <bool VF>
+static FixedFn fixed_h(int hc, int vc) {
+    switch (hc) {
+    case 2: return fixed_v<VF, 2>(vc);
+    case 4: return fixed_v<VF, 4>(vc);
+    case 6: return fixed_v<VF, 6>(vc);
+    default: return fixed_v<VF, 8>(vc);
+    }
+}
+static int fixed_class(int widest) { return widest <= 2 ? 2 : widest <= 4 ? 4 : widest <= 6 ? 6 : 8; }
+
 typedef void (*TiledFn)(const uint32_t *, uint32_t *, ResampleParams, TileGeom);
 template <bool VF, int HW>
 static TiledFn pick_v(int vclass) {
@@ -391,11 +562,47 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
         resample_copy_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, P);
     } else {
         if (n_frames > 65535) return ctx->fail(B200TIMG_EINVAL, "scale: too many frames for one launch");
+        // fast path: both axes need <= 8 taps -> fixed-tap kernel on 64x16 tiles
+        if (pl->h.widest <= 8 && pl->v.widest <= 8 && !getenv("B200TIMG_NO_FIXED")) {
+            const int hc = fixed_class(pl->h.widest), vc = fixed_class(pl->v.widest);
+            const int ntx = (ow + FTW - 1) / FTW, nty = (oh + FTH - 1) / FTH;
+            std::vector<int32_t> tix(ntx), tiy(nty);
+            int nix = 1, niy = 1;
+            for (int j = 0; j < ntx; ++j) {
+                int lo = 0x7fffffff, hi = -1;
+                for (int x = j * FTW; x < std::min(ow, (j + 1) * FTW); ++x) { lo = std::min(lo, pl->h.first[x]); hi = std::max(hi, pl->h.first[x] + hc - 1); }
+                tix[j] = lo; nix = std::max(nix, hi - lo + 1);
+            }
+            for (int j = 0; j < nty; ++j) {
+                int lo = 0x7fffffff, hi = -1;
+                for (int y = j * FTH; y < std::min(oh, (j + 1) * FTH); ++y) { lo = std::min(lo, pl->v.first[y]); hi = std::max(hi, pl->v.first[y] + vc - 1); }
+                tiy[j] = lo; niy = std::max(niy, hi - lo + 1);
+            }
+            const size_t fsmem = sizeof(float4) * ((size_t)nix * niy + (pl->vertical_first ? (size_t)FTH * nix : (size_t)niy * FTW))
+                               + sizeof(int) * (FTW + FTH) + sizeof(float) * ((size_t)FTW * (hc + 1) + (size_t)FTH * (vc + 1));
+            if (fsmem <= 100 * 1024) {
+                // tile origins live behind the tap tables in ctx->misc (re-uploaded per call: a few hundred bytes)
+                B2_CUDA(ctx, ctx->misc.reserve(4096 + sizeof(int32_t) * (size_t)(ntx + nty)));
+                int32_t *d_t = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 4096);
+                // re-uploaded per call (a few hundred bytes from pageable memory, stream-ordered)
+                B2_CUDA(ctx, cudaMemcpyAsync(d_t, tix.data(), sizeof(int32_t) * ntx, cudaMemcpyHostToDevice, ctx->stream));
+                B2_CUDA(ctx, cudaMemcpyAsync(d_t + ntx, tiy.data(), sizeof(int32_t) * nty, cudaMemcpyHostToDevice, ctx->stream));
+                FixedGeom FG{nix, niy, d_t, d_t + ntx};
+                FixedFn fn = pl->vertical_first ? fixed_h<true>(hc, vc) : fixed_h<false>(hc, vc);
+                B2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                const dim3 grid(ntx, nty, n_frames);
+                B2_KERNEL(ctx, "resample_fixed_kernel");
+                fn<<<grid, RT, fsmem, ctx->stream>>>(in, out, P, FG);
+                B2_LAUNCH_CHECK(ctx);
+                return B200TIMG_OK;
+            }
+        }
         // tile shape: largest of a few candidates whose decoded window + intermediate fit in shared memory
         static const int cand[][2] = {{64, 16}, {32, 16}, {32, 8}, {16, 8}, {8, 4}};
         TileGeom G{0, 0, 0, 0};
         size_t smem = 0;
-        const size_t smem_budget = 74 * 1024;      // 3 CTAs/SM
+        size_t smem_budget = 74 * 1024;      // 3 CTAs/SM
+        if (const char *e = getenv("B200TIMG_TILE_SMEM_KB")) smem_budget = (size_t)atoi(e) * 1024;   // tuning knob
         for (const auto &c : cand) {
             int nix = 1, niy = 1;
             for (int x0 = 0; x0 < ow; x0 += c[0]) {
