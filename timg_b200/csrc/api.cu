@@ -1,6 +1,8 @@
 // The extern "C" surface declared in include/b200timg.h: context management, host-buffer
 // entry points (upload -> kernels -> download) and the batched pipelines.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -64,6 +66,12 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     ctx->out_stage.release(); ctx->offsets.release(); ctx->cells.release(); ctx->rows.release();
     ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release();
     ctx->pinned.release(); ctx->pinned_io.release();
+    for (int i = 0; i < 2; ++i) { ctx->pipe_in[i].release(); ctx->pipe_out[i].release(); }
+    if (ctx->pipe_ready) {
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_write[i]); cudaEventDestroy(ctx->ev_d2h[i]); }
+        cudaEventDestroy(ctx->ev_prep);
+        cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->d2h_stream);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->plan) free_plan(ctx->plan);
     delete ctx;
@@ -361,38 +369,89 @@ int b200timg_sixel_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const u
     return sixel_batch_phases(ctx, b, d_src, d_out, out_cap, d_offsets, 3);
 }
 
+static int pipe_init(b200timg_ctx *ctx) {
+    if (ctx->pipe_ready) return B200TIMG_OK;
+    B2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    B2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
+        B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_write[i], cudaEventDisableTiming));
+        B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+    }
+    B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_prep, cudaEventDisableTiming));
+    ctx->pipe_ready = true;
+    return B200TIMG_OK;
+}
+
+// Host-buffer batch: the batch is cut into chunks; while chunk k runs its kernels, chunk k+1 is
+// uploading and chunk k-1's encoded bytes are downloading (three streams, double-buffered staging).
+// Per chunk the encoded size is known before anything is written (sixel) or bounded (blocks), so
+// the caller's buffer is never overrun and *exactly* the encoded bytes cross PCIe on the way back.
 static int batch_host(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,
                       size_t out_cap, uint64_t *offsets, bool sixel) {
     B2_TRY(check_ctx(ctx));
     B2_TRY(validate_batch(ctx, b));
     if (!src || !out || !offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
-    const size_t in_bytes = (size_t)b->src_w * b->src_h * 4 * b->n_frames;
-    const size_t off_bytes = (size_t)(b->n_frames + 1) * sizeof(uint64_t);
-    B2_CUDA(ctx, ctx->in_stage.reserve(in_bytes));
-    B2_CUDA(ctx, ctx->offsets.reserve(off_bytes));
-    B2_TRY(upload(ctx, ctx->in_stage.p, src, in_bytes));
-    if (sixel) {
-        // sizes first (exact), then bytes: the encoded stream is sized before it is written
-        B2_TRY(sixel_batch_phases(ctx, b, ctx->in_stage.as<uint8_t>(), nullptr, 0, ctx->offsets.as<uint64_t>(), 1));
-        B2_TRY(download(ctx, offsets, ctx->offsets.p, off_bytes));
-        B2_TRY(sync(ctx));
-        const size_t total = (size_t)offsets[b->n_frames];
-        if (total > out_cap) return ctx->fail(B200TIMG_ENOSPC, "batch: need %zu bytes, have %zu", total, out_cap);
-        B2_CUDA(ctx, ctx->out_stage.reserve(total));
-        B2_TRY(sixel_batch_phases(ctx, b, nullptr, ctx->out_stage.as<char>(), total, ctx->offsets.as<uint64_t>(), 2));
-        B2_TRY(download(ctx, out, ctx->out_stage.p, total));
-        return sync(ctx);
+    B2_TRY(pipe_init(ctx));
+    const size_t frame_bytes = (size_t)b->src_w * b->src_h * 4;
+    int chunk = (int)std::max<size_t>(1, ((size_t)384 << 20) / frame_bytes);
+    if (const char *e = getenv("B200TIMG_CHUNK_FRAMES")) chunk = std::max(1, atoi(e));      // test knob
+    if (!sixel && b->animation) chunk = b->n_frames;          // delta frames chain through the whole batch
+    chunk = std::min(chunk, b->n_frames);
+    const int n_chunks = (b->n_frames + chunk - 1) / chunk;
+    const size_t blocks_bound = sixel ? 0 : b200timg_blocks_bound(b->out_w, b->out_h) * (size_t)chunk + 64;
+    for (int i = 0; i < 2 && i < n_chunks; ++i) B2_CUDA(ctx, ctx->pipe_in[i].reserve(frame_bytes * chunk));
+    B2_CUDA(ctx, ctx->offsets.reserve((size_t)(chunk + 1) * sizeof(uint64_t)));
+    B2_CUDA(ctx, ctx->pinned.reserve((size_t)(chunk + 1) * sizeof(uint64_t)));
+    uint64_t *h_offs = ctx->pinned.as<uint64_t>();
+
+    auto upload_chunk = [&](int k) -> int {
+        const int i = k & 1, f0 = k * chunk, nf = std::min(chunk, b->n_frames - f0);
+        B2_CUDA(ctx, cudaMemcpyAsync(ctx->pipe_in[i].p, src + (size_t)f0 * frame_bytes, frame_bytes * nf,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+        B2_CUDA(ctx, cudaEventRecord(ctx->ev_up[i], ctx->copy_stream));
+        return B200TIMG_OK;
+    };
+    B2_TRY(upload_chunk(0));
+    if (n_chunks > 1) B2_TRY(upload_chunk(1));
+    size_t base_bytes = 0;
+    offsets[0] = 0;
+    for (int k = 0; k < n_chunks; ++k) {
+        const int i = k & 1, f0 = k * chunk, nf = std::min(chunk, b->n_frames - f0);
+        b200timg_batch sub = *b;
+        sub.n_frames = nf;
+        const uint8_t *d_in = ctx->pipe_in[i].as<uint8_t>();
+        B2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[i], 0));
+        if (k >= 2) B2_CUDA(ctx, cudaEventSynchronize(ctx->ev_d2h[i]));            // pipe_out[i] is free again
+        if (sixel) {
+            B2_TRY(sixel_batch_phases(ctx, &sub, d_in, nullptr, 0, ctx->offsets.as<uint64_t>(), 1));
+        } else {
+            B2_CUDA(ctx, ctx->pipe_out[i].reserve(blocks_bound));
+            B2_TRY(b200timg_blocks_batch_dev(ctx, &sub, d_in, ctx->pipe_out[i].as<char>(), blocks_bound,
+                                             ctx->offsets.as<uint64_t>()));
+        }
+        B2_CUDA(ctx, cudaMemcpyAsync(h_offs, ctx->offsets.p, (size_t)(nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        B2_CUDA(ctx, cudaEventRecord(ctx->ev_prep, ctx->stream));
+        B2_CUDA(ctx, cudaEventSynchronize(ctx->ev_prep));                          // sizes of this chunk are on the host
+        const size_t total = (size_t)h_offs[nf];
+        for (int j = 1; j <= nf; ++j) offsets[f0 + j] = base_bytes + h_offs[j];
+        if (base_bytes + total > out_cap) {
+            cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->d2h_stream);
+            return ctx->fail(B200TIMG_ENOSPC, "batch: need more than %zu bytes (have %zu)", base_bytes + total, out_cap);
+        }
+        if (sixel) {
+            B2_CUDA(ctx, ctx->pipe_out[i].reserve(total));
+            B2_TRY(sixel_batch_phases(ctx, &sub, nullptr, ctx->pipe_out[i].as<char>(), total, ctx->offsets.as<uint64_t>(), 2));
+        }
+        B2_CUDA(ctx, cudaEventRecord(ctx->ev_write[i], ctx->stream));
+        if (k + 2 < n_chunks) B2_TRY(upload_chunk(k + 2));                         // pipe_in[i] was consumed by this chunk's scale
+        B2_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_write[i], 0));
+        if (total) B2_CUDA(ctx, cudaMemcpyAsync(out + base_bytes, ctx->pipe_out[i].p, total, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        B2_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[i], ctx->d2h_stream));
+        base_bytes += total;
     }
-    const size_t bound = b200timg_blocks_bound(b->out_w, b->out_h) * b->n_frames + 64;
-    B2_CUDA(ctx, ctx->out_stage.reserve(bound));
-    B2_TRY(b200timg_blocks_batch_dev(ctx, b, ctx->in_stage.as<uint8_t>(), ctx->out_stage.as<char>(), bound,
-                                     ctx->offsets.as<uint64_t>()));
-    B2_TRY(download(ctx, offsets, ctx->offsets.p, off_bytes));
-    B2_TRY(sync(ctx));
-    const size_t total = (size_t)offsets[b->n_frames];
-    if (total > out_cap) return ctx->fail(B200TIMG_ENOSPC, "batch: need %zu bytes, have %zu", total, out_cap);
-    if (total) { B2_TRY(download(ctx, out, ctx->out_stage.p, total)); B2_TRY(sync(ctx)); }
-    return B200TIMG_OK;
+    B2_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+    return sync(ctx);
 }
 
 int b200timg_blocks_batch(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,

@@ -81,6 +81,11 @@ struct b200timg_ctx {
     b200timg::DevBuf misc;         // small flags / sizes
     b200timg::HostBuf pinned;      // staging for sizes / offsets
     b200timg::HostBuf pinned_io;   // staging for pageable payloads
+    // host-batch pipeline: upload of chunk k+1 / download of chunk k-1 overlap the kernels of chunk k
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_write[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_prep = nullptr;
+    b200timg::DevBuf pipe_in[2], pipe_out[2];
+    bool pipe_ready = false;
 
     int fail(int code, const char *fmt, ...) {
         va_list ap; va_start(ap, fmt);
