@@ -432,16 +432,27 @@ sixel_dither_kernel(const uint32_t *__restrict__ fb, int w, int h, int nwarps, S
 
 // ---- emit ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ndig_u(uint32_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
-__device__ __forceinline__ uint32_t rle_len(uint32_t n) { return n == 0 ? 0 : (n > 3 ? 2 + ndig_u(n) : n); }   // tosixel.c sixel_put_flash
 __device__ __forceinline__ char *put_num_u(char *o, uint32_t v) {
     char tmp[10]; int n = 0;
     do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
     while (n) *o++ = tmp[--n];
     return o;
 }
+// Branch-light formatting for values < 10000 (run lengths, gaps and colour numbers are bounded by
+// the frame width <= 4095 and 255): no loops, so lanes of a warp do not serialise on digit counts.
+__device__ __forceinline__ uint32_t ndig4(uint32_t v) { return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u); }
+__device__ __forceinline__ char *put_num4(char *o, uint32_t v) {
+    const uint32_t d3 = v / 1000u, r3 = v - d3 * 1000u, d2 = r3 / 100u, r2 = r3 - d2 * 100u, d1 = r2 / 10u, d0 = r2 - d1 * 10u;
+    if (v >= 1000u) *o++ = (char)('0' + d3);
+    if (v >= 100u) *o++ = (char)('0' + d2);
+    if (v >= 10u) *o++ = (char)('0' + d1);
+    *o++ = (char)('0' + d0);
+    return o;
+}
+__device__ __forceinline__ uint32_t rle_len(uint32_t n) { return n > 3u ? 2u + ndig4(n) : n; }   // tosixel.c sixel_put_flash
 __device__ __forceinline__ char *put_rle(char *o, uint32_t n, char ch) {
-    if (n > 3) { *o++ = '!'; o = put_num_u(o, n); *o++ = ch; }
-    else for (uint32_t i = 0; i < n; ++i) *o++ = ch;
+    if (n > 3u) { *o++ = '!'; o = put_num4(o, n); *o++ = ch; }
+    else { if (n > 0u) *o++ = ch; if (n > 1u) *o++ = ch; if (n > 2u) *o++ = ch; }
     return o;
 }
 
@@ -451,23 +462,25 @@ __device__ __forceinline__ uint32_t ent_pack(uint32_t c, uint32_t x, uint32_t bi
 
 struct EmitGeom { int w, h, cols_per_warp; };
 
-// The <=6 distinct (colour, bits) pairs of column x of a 6-row band.
-__device__ __forceinline__ int column_entries(const uint8_t *__restrict__ idx, int w, int x, uint32_t *col, uint32_t *bits) {
-    uint32_t c[6];
+// The <=6 distinct (colour, bits) pairs of column x of a 6-row band: slot i is valid iff row i is the
+// first row showing its colour (fixed slots, so everything stays in registers).  Returns the valid mask.
+__device__ __forceinline__ uint32_t column_entries(const uint8_t *__restrict__ idx, int w, int x, uint32_t *c, uint32_t *bits) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) c[i] = idx[(long long)i * w + x];
-    int ns = 0;
+    uint32_t valid = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         bool seen = false;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) if (j < i && c[j] == c[i]) seen = true;
         uint32_t b = 0;
 #pragma unroll
-        for (int j = 0; j < 6; ++j) if (j >= i && c[j] == c[i]) b |= 1u << j;
-        if (!seen) { col[ns] = c[i]; bits[ns] = b; ++ns; }
+        for (int j = 0; j < 6; ++j) {
+            if (j < i && c[j] == c[i]) seen = true;
+            if (j >= i && c[j] == c[i]) b |= 1u << j;
+        }
+        bits[i] = b;
+        if (!seen) valid |= 1u << i;
     }
-    return ns;
+    return valid;
 }
 
 // bytes the entry at sorted position i contributes (0 unless it starts a run); also returns the
@@ -487,7 +500,7 @@ __device__ __forceinline__ RunInfo run_info(const uint32_t *sorted, int i, int n
     while (i + (int)L < n && sorted[i + L] == e + (L << 6)) ++L;                     // same colour, x+L, same bits
     r.len = L;
     r.gap = has_prev ? x - ((p >> 6) & 4095) - 1 : x;
-    r.bytes = rle_len(r.gap) + rle_len(L) + (has_prev ? 0 : 1 + ndig_u(r.c) + (r.c != minc ? 1 : 0));
+    r.bytes = rle_len(r.gap) + rle_len(L) + (has_prev ? 0 : 1 + ndig4(r.c) + (r.c != minc ? 1 : 0));
     return r;
 }
 
@@ -497,10 +510,9 @@ __device__ __forceinline__ RunInfo run_info(const uint32_t *sorted, int i, int n
 __global__ void __launch_bounds__(ET)
 sixel_emit_kernel(EmitGeom G, SixelWork W) {
     extern __shared__ uint32_t s_sorted[];                   // [6*w]
-    __shared__ unsigned short s_cnt[EW][256];
+    __shared__ uint32_t s_cnt[EW][256];
     __shared__ uint32_t s_mask[EW * 256];
     __shared__ uint32_t s_w[ET / 32];
-    __shared__ uint32_t s_colbase[256];
     const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int w = G.w;
     const SixelFrameHdr *hdr = W.hdr + f;
@@ -509,22 +521,14 @@ sixel_emit_kernel(EmitGeom G, SixelWork W) {
     for (int i = tid; i < EW * 256; i += ET) { (&s_cnt[0][0])[i] = 0; s_mask[i] = 0; }
     __syncthreads();
 
-    // (1a) count entries per (warp, colour)
+    // (1a) count entries per (warp, colour): shared-memory atomics, a few per column
     const int x_lo = wid * G.cols_per_warp, x_hi = min(w, x_lo + G.cols_per_warp);
-    for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
-        const int x = x0 + lane;
+    uint32_t *cnt = s_cnt[wid];
+    for (int x = x_lo + lane; x < x_hi; x += 32) {
         uint32_t col[6], bits[6];
-        const int ns = x < x_hi ? column_entries(idx, w, x, col, bits) : 0;
+        const uint32_t valid = column_entries(idx, w, x, col, bits);
 #pragma unroll
-        for (int s = 0; s < 6; ++s) {
-            const bool have = s < ns;
-            const uint32_t vm = __ballot_sync(0xffffffffu, have);
-            if (have) {
-                const uint32_t m = __match_any_sync(vm, col[s]);
-                if ((m & ((1u << lane) - 1)) == 0) s_cnt[wid][col[s]] += (unsigned short)__popc(m);
-            }
-            __syncwarp();
-        }
+        for (int s = 0; s < 6; ++s) if (valid & (1u << s)) atomicAdd(&cnt[col[s]], 1u);
     }
     __syncthreads();
     // per-colour totals -> colour bases -> per (warp, colour) start offsets (in place)
@@ -532,40 +536,33 @@ sixel_emit_kernel(EmitGeom G, SixelWork W) {
     if (tid < 256) for (int k = 0; k < EW; ++k) tot_c += s_cnt[k][tid];
     uint32_t n_ent; const uint32_t cb = block_excl_scan<ET>(tid < 256 ? tot_c : 0, s_w, n_ent);
     if (tid < 256) {
-        s_colbase[tid] = cb;
         uint32_t run = cb;
-        for (int k = 0; k < EW; ++k) { const uint32_t v = s_cnt[k][tid]; s_cnt[k][tid] = (unsigned short)run; run += v; }
+        for (int k = 0; k < EW; ++k) { const uint32_t v = s_cnt[k][tid]; s_cnt[k][tid] = run; run += v; }
     }
     __syncthreads();
-    // (1b) scatter.  Ranks must follow x; inside one 32-column step a colour can sit in different
-    // slots of different columns, so the lanes holding each colour are first collected in a per-warp
-    // mask table and the rank is the number of lower lanes in that mask.
+    // (1b) scatter.  Ranks must follow x: per 32-column step the lanes holding each colour are
+    // collected in a per-warp mask table (one atomicOr per entry); an entry's rank is the number of
+    // lower lanes in its colour's mask, and the lowest lane advances the (warp, colour) cursor.
     uint32_t *M = s_mask + wid * 256;
+    const uint32_t lt = (1u << lane) - 1;
     for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
         const int x = x0 + lane;
         uint32_t col[6], bits[6];
-        const int ns = x < x_hi ? column_entries(idx, w, x, col, bits) : 0;
+        const uint32_t valid = x < x_hi ? column_entries(idx, w, x, col, bits) : 0u;
 #pragma unroll
-        for (int s = 0; s < 6; ++s) {
-            const bool have = s < ns;
-            const uint32_t vm = __ballot_sync(0xffffffffu, have);
-            if (have) {
-                const uint32_t m = __match_any_sync(vm, col[s]);
-                if ((m & ((1u << lane) - 1)) == 0) M[col[s]] |= m;
-            }
-            __syncwarp();
-        }
+        for (int s = 0; s < 6; ++s) if (valid & (1u << s)) atomicOr(&M[col[s]], 1u << lane);
+        __syncwarp();
         uint32_t mk[6];
 #pragma unroll
         for (int s = 0; s < 6; ++s)
-            if (s < ns) {
+            if (valid & (1u << s)) {
                 mk[s] = M[col[s]];
-                s_sorted[s_cnt[wid][col[s]] + __popc(mk[s] & ((1u << lane) - 1))] = ent_pack(col[s], (uint32_t)x, bits[s]);
+                s_sorted[cnt[col[s]] + __popc(mk[s] & lt)] = ent_pack(col[s], (uint32_t)x, bits[s]);
             }
         __syncwarp();
 #pragma unroll
         for (int s = 0; s < 6; ++s)
-            if (s < ns && (mk[s] & ((1u << lane) - 1)) == 0) { s_cnt[wid][col[s]] += (unsigned short)__popc(mk[s]); M[col[s]] = 0; }
+            if ((valid & (1u << s)) && (mk[s] & lt) == 0) { cnt[col[s]] += (uint32_t)__popc(mk[s]); M[col[s]] = 0; }
         __syncwarp();
     }
     __syncthreads();
@@ -582,7 +579,7 @@ sixel_emit_kernel(EmitGeom G, SixelWork W) {
     for (int i = lo; i < hi; ++i) {
         const RunInfo r = run_info(s_sorted, i, n, minc);
         if (!r.bytes) continue;
-        if (r.first_of_colour) { if (r.c != minc) *o++ = '$'; *o++ = '#'; o = put_num_u(o, r.c); }
+        if (r.first_of_colour) { if (r.c != minc) *o++ = '$'; *o++ = '#'; o = put_num4(o, r.c); }
         o = put_rle(o, r.gap, '?');
         o = put_rle(o, r.len, (char)('?' + r.bits));
     }
@@ -726,7 +723,7 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
 
     static bool attrs_set = false;
     EmitGeom G; G.w = w; G.h = h; G.cols_per_warp = ((w + EW - 1) / EW + 31) / 32 * 32;
-    const size_t smem_limit = 227 * 1024 - 30 * 1024;   // the emit kernel also has ~26 KB of static shared memory
+    const size_t smem_limit = 227 * 1024 - 36 * 1024;   // the emit kernel also has ~33 KB of static shared memory
     const size_t emit_smem = sizeof(uint32_t) * (size_t)6 * w;
     if (w > 4095 || emit_smem > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
     if (!attrs_set) {
