@@ -300,7 +300,22 @@ __device__ __forceinline__ int fs_tap(int v, int e, int k) {      // error_diffu
     const int q = (t + ((t >> 31) & 15)) >> 4;                  // C division truncates toward zero
     return min(255, max(0, v + q));
 }
-constexpr int DW_MAX = 32;     // warps per frame CTA (upper bound; the launch picks how many)
+// One pixel's quantisation error, unpacked: e[c] in [-255,255] and bias[c] = (e<0 ? 15 : 0), so that
+// error_diffuse()'s  e*k/16 (C truncation)  is  (e*k + bias) >> 4  -- one IMAD and one shift per tap.
+struct FsErr {
+    int e[3], b[3];
+    __device__ __forceinline__ void zero() { e[0] = e[1] = e[2] = 0; b[0] = b[1] = b[2] = 0; }
+    __device__ __forceinline__ void set(int r, int g, int bl) {
+        e[0] = r; e[1] = g; e[2] = bl;
+        b[0] = (r >> 31) & 15; b[1] = (g >> 31) & 15; b[2] = (bl >> 31) & 15;
+    }
+    __device__ __forceinline__ void unpack(uint32_t p) { set((int)(p & 511) - 256, (int)((p >> 9) & 511) - 256, (int)((p >> 18) & 511) - 256); }
+    __device__ __forceinline__ uint32_t pack() const { return (uint32_t)(e[0] + 256) | ((uint32_t)(e[1] + 256) << 9) | ((uint32_t)(e[2] + 256) << 18); }
+};
+__device__ __forceinline__ int fs_add(int v, const FsErr &er, int c, int k) {
+    return min(255, max(0, v + ((er.e[c] * k + er.b[c]) >> 4)));
+}
+constexpr int DW_MAX = 24;     // warps per frame CTA (upper bound; the launch picks how many)
 constexpr int DCH = 16;        // columns per staged chunk
 constexpr int DIN_STRIDE = DCH + 1;              // u32 words per staged row (odd: lanes hit distinct banks)
 constexpr int DOUT_STRIDE = 20;                  // bytes per staged output row (5 words: conflict-free)
@@ -341,7 +356,9 @@ sixel_dither_kernel(const uint32_t *__restrict__ fb, int w, int h, int nwarps, S
         const bool last_row = (y == h - 1);
         const uint32_t *bin = band > 0 ? bnd + (long long)(band - 1) * w : nullptr;
         uint32_t *bout = bnd + (long long)band * w;
-        uint32_t last_e = EZ, up_m1 = EZ, up_0 = EZ, up_p1 = EZ, own = EZ, e_first = EZ;
+        uint32_t last_e = EZ;
+        FsErr up_m1, up_0, up_p1, own, e_first;
+        up_m1.zero(); up_0.zero(); up_p1.zero(); own.zero(); e_first.zero();
         const int steps = w + 62, nchunks = (steps + DCH - 1) / DCH;
         // pre-skewed load of chunk c into registers: element i covers tile row 2i+hrow, column hcol
         uint32_t pre[16];
@@ -369,45 +386,72 @@ sixel_dither_kernel(const uint32_t *__restrict__ fb, int w, int h, int nwarps, S
                 __syncwarp();
                 const int bx = t0 + 1 + lane;                     // lane 0 consumes bin[t+1] at step t
                 if (lane < DCH && bx < w) binreg = __ldcg(bin + bx);
-                if (c == 0 && lane == 0) up_p1 = __ldcg(bin);     // e(0, y-1): lane 0 has no warm-up step
+                if (c == 0 && lane == 0) up_p1.unpack(__ldcg(bin));   // e(0, y-1): lane 0 has no warm-up step
             }
             const uint32_t *tin = s_in + (c & 1) * 32 * DIN_STRIDE + lane * DIN_STRIDE;
             uint32_t bkeep = EZ;
+            // interior chunk: every lane is strictly inside its row for all DCH steps and no lane runs the
+            // frame's last row -> the step needs no range checks and always diffuses
+            const bool interior = (t0 - 62 >= 1) && (t0 + DCH - 1 <= w - 2) && (band * 32 + 31 < h - 1);
+            if (interior) {
 #pragma unroll 4
-            for (int j = 0; j < DCH; ++j) {
-                const int t = t0 + j, x = t - 2 * lane;
-                uint32_t recv = __shfl_up_sync(0xffffffffu, last_e, 1);
-                const uint32_t b0 = __shfl_sync(0xffffffffu, binreg, j);
-                if (lane == 0) recv = b0;
-                up_m1 = up_0; up_0 = up_p1; up_p1 = recv;
-                uint32_t ci = 0;
-                if (x >= 0 && x < w && row_ok) {
+                for (int j = 0; j < DCH; ++j) {
+                    uint32_t recv = __shfl_up_sync(0xffffffffu, last_e, 1);
+                    const uint32_t b0 = __shfl_sync(0xffffffffu, binreg, j);
+                    if (lane == 0) recv = b0;
+                    up_m1 = up_0; up_0 = up_p1; up_p1.unpack(recv);
                     const uint32_t px = tin[j];
                     int v[3] = {(int)(px & 0xff), (int)((px >> 8) & 0xff), (int)((px >> 16) & 0xff)};
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        const int sh = 9 * ch;
-                        v[ch] = fs_tap(v[ch], (int)((up_m1 >> sh) & 511) - 256, 1);      // from (x-1, y-1)
-                        v[ch] = fs_tap(v[ch], (int)((up_0 >> sh) & 511) - 256, 5);       // from (x,   y-1)
-                        v[ch] = fs_tap(v[ch], (int)((up_p1 >> sh) & 511) - 256, 3);      // from (x+1, y-1)
-                        if (x == w - 1) v[ch] = fs_tap(v[ch], (int)((e_first >> sh) & 511) - 256, 3);   // libsixel: (0,y)'s below-left tap
-                        v[ch] = fs_tap(v[ch], (int)((own >> sh) & 511) - 256, 7);        // from (x-1, y)
+                        v[ch] = fs_add(v[ch], up_m1, ch, 1);
+                        v[ch] = fs_add(v[ch], up_0, ch, 5);
+                        v[ch] = fs_add(v[ch], up_p1, ch, 3);
+                        v[ch] = fs_add(v[ch], own, ch, 7);
                     }
                     const uint32_t cell = ((uint32_t)(v[0] >> 3) << 10) | ((uint32_t)(v[1] >> 3) << 5) | (uint32_t)(v[2] >> 3);
-                    ci = s_lut[cell];
+                    const uint32_t ci = s_lut[cell];
                     const uint32_t pal = s_pal[ci];
-                    uint32_t e = EZ;
-                    if (x < w - 1 && !last_row)
-                        e = (uint32_t)(v[0] - (int)(pal & 0xff) + 256) | ((uint32_t)(v[1] - (int)((pal >> 8) & 0xff) + 256) << 9)
-                          | ((uint32_t)(v[2] - (int)((pal >> 16) & 0xff) + 256) << 18);
-                    if (x == 0) e_first = e;
-                    own = e; last_e = e;
-                } else if (x >= w) {
-                    last_e = EZ;
+                    own.set(v[0] - (int)(pal & 0xff), v[1] - (int)((pal >> 8) & 0xff), v[2] - (int)((pal >> 16) & 0xff));
+                    last_e = own.pack();
+                    s_out[lane * DOUT_STRIDE + j] = (uint8_t)ci;
+                    const uint32_t e31 = __shfl_sync(0xffffffffu, last_e, 31);
+                    if (lane == j) bkeep = e31;
                 }
-                s_out[lane * DOUT_STRIDE + j] = (uint8_t)ci;
-                const uint32_t e31 = __shfl_sync(0xffffffffu, last_e, 31);      // the band's last row, column t-62
-                if (lane == j) bkeep = e31;
+            } else {
+#pragma unroll 2
+                for (int j = 0; j < DCH; ++j) {
+                    const int t = t0 + j, x = t - 2 * lane;
+                    uint32_t recv = __shfl_up_sync(0xffffffffu, last_e, 1);
+                    const uint32_t b0 = __shfl_sync(0xffffffffu, binreg, j);
+                    if (lane == 0) recv = b0;
+                    up_m1 = up_0; up_0 = up_p1; up_p1.unpack(recv);
+                    uint32_t ci = 0;
+                    if (x >= 0 && x < w && row_ok) {
+                        const uint32_t px = tin[j];
+                        int v[3] = {(int)(px & 0xff), (int)((px >> 8) & 0xff), (int)((px >> 16) & 0xff)};
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            v[ch] = fs_add(v[ch], up_m1, ch, 1);                       // from (x-1, y-1)
+                            v[ch] = fs_add(v[ch], up_0, ch, 5);                        // from (x,   y-1)
+                            v[ch] = fs_add(v[ch], up_p1, ch, 3);                       // from (x+1, y-1)
+                            if (x == w - 1) v[ch] = fs_add(v[ch], e_first, ch, 3);     // libsixel: (0,y)'s below-left tap
+                            v[ch] = fs_add(v[ch], own, ch, 7);                         // from (x-1, y)
+                        }
+                        const uint32_t cell = ((uint32_t)(v[0] >> 3) << 10) | ((uint32_t)(v[1] >> 3) << 5) | (uint32_t)(v[2] >> 3);
+                        ci = s_lut[cell];
+                        const uint32_t pal = s_pal[ci];
+                        if (x < w - 1 && !last_row) own.set(v[0] - (int)(pal & 0xff), v[1] - (int)((pal >> 8) & 0xff), v[2] - (int)((pal >> 16) & 0xff));
+                        else own.zero();
+                        if (x == 0) e_first = own;
+                        last_e = own.pack();
+                    } else if (x >= w) {
+                        last_e = EZ;
+                    }
+                    s_out[lane * DOUT_STRIDE + j] = (uint8_t)ci;
+                    const uint32_t e31 = __shfl_sync(0xffffffffu, last_e, 31);      // the band's last row, column t-62
+                    if (lane == j) bkeep = e31;
+                }
             }
             __syncwarp();
             // write this chunk's indices: half-warp per row, 16 contiguous bytes
