@@ -135,17 +135,19 @@ resample_direct_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
 // pixel run a second pass for them.
 struct TileGeom { int tw, th, nix_max, niy_max; };
 
+// byte k of p as a float without the (quarter-rate) I2F unit: 0x4B0000bb is 2^23 + bb exactly.
+__device__ __forceinline__ float byte_f(uint32_t p, int k) {
+    return fsub(__uint_as_float(__byte_perm(p, 0x4B000000u, 0x7540u | (uint32_t)k)), 8388608.0f);
+}
 __device__ __forceinline__ float4 decode_pm(uint32_t p, int bgra) {       // (R*A, G*A, B*A, A)
     const float k = 1.0f / 255.0f;
-    const float c0 = fmul((float)(p & 0xff), k), c1 = fmul((float)((p >> 8) & 0xff), k);
-    const float c2 = fmul((float)((p >> 16) & 0xff), k), a = fmul((float)(p >> 24), k);
+    const float c0 = fmul(byte_f(p, 0), k), c1 = fmul(byte_f(p, 1), k), c2 = fmul(byte_f(p, 2), k), a = fmul(byte_f(p, 3), k);
     const float r = bgra ? c2 : c0, b = bgra ? c0 : c2;
     return make_float4(fmul(r, a), fmul(c1, a), fmul(b, a), a);
 }
 __device__ __forceinline__ float4 decode_plain(uint32_t p, int bgra) {    // (R, G, B, -)
     const float k = 1.0f / 255.0f;
-    const float c0 = fmul((float)(p & 0xff), k), c1 = fmul((float)((p >> 8) & 0xff), k);
-    const float c2 = fmul((float)((p >> 16) & 0xff), k);
+    const float c0 = fmul(byte_f(p, 0), k), c1 = fmul(byte_f(p, 1), k), c2 = fmul(byte_f(p, 2), k);
     return make_float4(bgra ? c2 : c0, c1, bgra ? c0 : c2, 0.0f);
 }
 __device__ __forceinline__ float4 mul4(float4 v, float w) { return make_float4(fmul(v.x, w), fmul(v.y, w), fmul(v.z, w), fmul(v.w, w)); }
@@ -342,16 +344,31 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
     float4 res[4], plain[4];
     bool need_plain = false;
     for (int pass = 0; pass < 2; ++pass) {
-        for (int ly = wid; ly < niy; ly += RT / 32) {
-            const int y = iy0 + ly;
-            const uint32_t *row = src + (long long)y * P.iw;
-            float4 *drow = Din + ly * nix;
-            for (int lx = lane; lx < nix; lx += 32) {
-                const int x = ix0 + lx;
-                const uint32_t p = (y < P.ih && x < P.iw) ? row[x] : 0u;
-                drow[lx] = pass == 0 ? decode_pm(p, P.bgra) : decode_plain(p, P.bgra);
+        // stage + decode the window once.  All of a thread's global loads (up to 4 rows x 4 column
+        // groups) are issued before the first one is consumed, so their latencies overlap.
+        for (int ly0 = 0; ly0 < niy; ly0 += 4 * (RT / 32))
+            for (int lx0 = 0; lx0 < nix; lx0 += 128) {
+                uint32_t pv[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int ly = ly0 + wid + r * (RT / 32), y = iy0 + ly;
+                    const uint32_t *row = src + (long long)y * P.iw + ix0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int lx = lx0 + lane + 32 * c;
+                        pv[r][c] = (ly < niy && lx < nix && y < P.ih && ix0 + lx < P.iw) ? row[lx] : 0u;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int ly = ly0 + wid + r * (RT / 32);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int lx = lx0 + lane + 32 * c;
+                        if (ly < niy && lx < nix) Din[ly * nix + lx] = pass == 0 ? decode_pm(pv[r][c], P.bgra) : decode_plain(pv[r][c], P.bgra);
+                    }
+                }
             }
-        }
         __syncthreads();
         float4 acc[4];
         if (VFIRST) {
