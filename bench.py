@@ -298,6 +298,12 @@ def main():
                 raise RuntimeError(L.b200timg_last_error(ctx.h).decode())
 
         e2e_step()
+        # raw pinned H2D rate of this box, for context: the e2e number cannot exceed it
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        frames[:min(Fe, 32)].copy_(h_in[:min(Fe, 32)], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        h2d_gbs = min(Fe, 32) * IW * IH * 4 / (time.perf_counter() - t0) / 1e9
         if world > 1:
             dist.barrier()
         ke = max(1, min(args.steps, 5))
@@ -312,7 +318,9 @@ def main():
         dt = float(tt.item())
         e2e = {"value": world * Fe * ke * IW * IH / 1e6 / dt, "unit": "Mpx/s",
                "h2d_bytes_per_step": int(Fe * IW * IH * 4), "d2h_bytes_per_step": int(h_offs[Fe]) + 8 * (Fe + 1),
-               "frames_per_step": Fe, "steps": ke, "api": "b200timg_sixel_batch (host buffers, pinned)"}
+               "frames_per_step": Fe, "steps": ke, "api": "b200timg_sixel_batch (host buffers, pinned)",
+               "pcie_h2d_gbs_measured": h2d_gbs,
+               "pcie_bound_mpx_s": h2d_gbs * 1e9 / 4 / 1e6}
         del h_in, h_out
 
     # ---- the reference's CPU path beside it (rank 0, N=1 only): a bounded sample

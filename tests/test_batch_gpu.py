@@ -74,3 +74,47 @@ def test_sixel_batch_too_small_buffer_reports_enospc(ctx):
     rc = timg_b200.lib().b200timg_sixel_batch(ctx.h, C.byref(b), frames.ctypes.data, out.ctypes.data, out.size,
                                                offs.ctypes.data)
     assert rc == timg_b200.ENOSPC
+
+
+def test_sixel_batch_c5_shape_unscaled_720p(ctx):
+    """C5 geometry: 1280x720 frames shown unscaled (copy-only scaler, height already a multiple of 6)."""
+    n, w, h = 3, 1280, 720
+    assert timg_b200.calc_fit(w, h, 2700, 1800, 9, 18) == (False, w, h)
+    frames = np.stack([synth.frame_np(200 + i, w, h, "photo") for i in range(n)])
+    outs = ctx.sixel_batch(frames, _batch(n, w, h, w, h))
+    for f in range(n):
+        img, used = oracle.sixel_decode(outs[f])
+        want, _ = oracle.sixel_decode(oracle.sixel_encode(frames[f], mode=1))
+        assert img.shape == (h, w, 3) and used <= 256
+        assert (img == want).all(), f
+
+
+def test_sixel_device_entry_matches_host_entry(ctx):
+    """b200timg_sixel_dev on device-resident frames == b200timg_sixel_encode frame by frame."""
+    import ctypes as C
+    import torch
+    n, w, h = 3, 200, 96
+    frames = np.stack([synth.frame_np(300 + i, w, h, "photo") for i in range(n)])
+    d = torch.tensor(frames).cuda()
+    out = torch.zeros(n * (4096 + 6 * w * h), dtype=torch.uint8, device="cuda")
+    offs = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    rc = timg_b200.lib().b200timg_sixel_dev(ctx.h, d.data_ptr(), w, h, n, out.data_ptr(), out.numel(), offs.data_ptr())
+    assert rc == 0
+    torch.cuda.synchronize()
+    o, ob = offs.cpu().numpy(), out.cpu().numpy()
+    for f in range(n):
+        assert ob[o[f]:o[f + 1]].tobytes() == ctx.sixel_encode(frames[f]), f
+
+
+def test_blocks_full_size_properties_4k_one_to_one(ctx):
+    """4K quarter-block frame (1:1): size-independent properties instead of an oracle run:
+    every row pair ends with ESC[0m LF, and re-encoding the same frame as a delta is empty."""
+    fb = synth.frame_np(9, 3840, 2160, "photo")
+    cv = B200BlockCanvas(ctx, True)
+    full = cv.send(fb)
+    assert full.count(b"\033[0m\n") == 1080
+    assert cv.send(fb, 0, -2160) == b""
+    fb2 = fb.copy()
+    fb2[1001, 2001] = (1, 2, 3, 255)
+    delta = cv.send(fb2, 0, -2160)
+    assert 0 < len(delta) < 200 and b"\033[1000C" in delta
