@@ -332,9 +332,8 @@ int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const 
     const size_t fb_bytes = (size_t)b->out_w * b->out_h * 4 * b->n_frames;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(fb_bytes));
     uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
-    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, b->out_h, b->n_frames));
-    B2_TRY(launch_compose(ctx, d_fb, b->out_w, b->out_h, b->n_frames, b->has_bg, b->bg, b->pattern,
-                          b->pattern_w, b->pattern_h, 0));
+    const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
+    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, b->out_h, b->n_frames, &cs));
     return launch_blocks(ctx, d_fb, nullptr, b->animation ? 2 : 0, b->out_w, b->out_h, b->n_frames, b->flags,
                          b->x_indent_cells, d_out, out_cap, d_offsets);
 }
@@ -351,13 +350,17 @@ static int sixel_batch_phases(b200timg_ctx *ctx, const b200timg_batch *b, const 
     const size_t frame_bytes = (size_t)b->out_w * hp * 4;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(frame_bytes * b->n_frames));
     uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
-    if (hp != b->out_h) B2_CUDA(ctx, cudaMemsetAsync(d_fb, 0, frame_bytes * b->n_frames, ctx->stream));
-    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, hp, b->n_frames));
-    // sources compose the image itself first (e.g. src/stb-image-source.cc:56-60) ...
-    // (start_row 0 over the real rows; the pad rows are transparent so they get bg too,
-    //  which is exactly what the canvas' own start_row=h call (:115-118) produces.)
-    B2_TRY(launch_compose(ctx, d_fb, b->out_w, hp, b->n_frames, b->has_bg, b->bg, b->pattern, b->pattern_w,
-                          b->pattern_h, 0));
+    // scale with AlphaComposeBackground fused into the epilogue (what the sources do, e.g.
+    // src/stb-image-source.cc:56-60); then only the pad strip is cleared and composed, exactly the
+    // canvas' own start_row = height call (src/sixel-canvas.cc:115-118).
+    const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
+    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, hp, b->n_frames, &cs));
+    if (hp != b->out_h) {
+        B2_CUDA(ctx, cudaMemset2DAsync(d_fb + (size_t)b->out_h * b->out_w * 4, frame_bytes, 0,
+                                       (size_t)(hp - b->out_h) * b->out_w * 4, b->n_frames, ctx->stream));
+        B2_TRY(launch_compose(ctx, d_fb, b->out_w, hp, b->n_frames, b->has_bg, b->bg, b->pattern, b->pattern_w,
+                              b->pattern_h, b->out_h));
+    }
     return launch_sixel(ctx, d_fb, b->out_w, hp, b->n_frames, d_out, out_cap, d_offsets, phases);
 }
 

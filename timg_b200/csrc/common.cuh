@@ -159,6 +159,41 @@ __device__ __forceinline__ uint32_t pack_rgba(uint32_t r, uint32_t g, uint32_t b
     return r | (g << 8) | (b << 16) | (a << 24);
 }
 
+// LinearColor::AlphaBlend + repack (src/framebuffer.h:142-161,169-172) of one RGBA8 pixel onto a
+// linearised background colour; opaque pixels pass through.
+__device__ __forceinline__ uint32_t blend_px(uint32_t p, float bgr, float bgg, float bgb) {
+    const uint32_t a8 = p >> 24;
+    if (a8 == 0xffu) return p;
+    const uint32_t r8 = p & 0xff, g8 = (p >> 8) & 0xff, b8 = (p >> 16) & 0xff;
+    const float a = (float)a8, ia = (float)(0xff - a8);
+    const float r = fdiv(fadd(fmul((float)(r8 * r8), a), fmul(bgr, ia)), 255.0f);
+    const float g = fdiv(fadd(fmul((float)(g8 * g8), a), fmul(bgg, ia)), 255.0f);
+    const float b = fdiv(fadd(fmul((float)(b8 * b8), a), fmul(bgb, ia)), 255.0f);
+    return pack_rgba(ungamma(r), ungamma(g), ungamma(b), 0xffu);
+}
+
+// What AlphaComposeBackground would do to a pixel at (x, y): resolved once on the host.
+struct ComposeSpec {
+    int active;                  // 0: leave pixels alone (no getter, transparent bg)
+    int use_pattern, pw, ph;
+    float bg[2][3];              // linearised background and pattern colours
+};
+inline ComposeSpec make_compose_spec(int has_bg, uint32_t bg, uint32_t pattern, int pw, int ph) {
+    ComposeSpec c;
+    c.active = (has_bg && (bg >> 24) != 0) ? 1 : 0;                       // src/framebuffer.cc:111,121
+    c.use_pattern = !((pattern >> 24) == 0 || pattern == bg || pw <= 0 || ph <= 0);   // :124-125
+    c.pw = pw > 0 ? pw : 1; c.ph = ph > 0 ? ph : 1;
+    const uint32_t cols[2] = {bg, pattern};
+    for (int k = 0; k < 2; ++k)
+        for (int ch = 0; ch < 3; ++ch) { const uint32_t v = (cols[k] >> (8 * ch)) & 0xff; c.bg[k][ch] = (float)(v * v); }
+    return c;
+}
+__device__ __forceinline__ uint32_t compose_at(const ComposeSpec &c, uint32_t p, int x, int y) {
+    if (!c.active || (p >> 24) == 0xffu) return p;
+    const int sel = c.use_pattern ? (((x / c.pw) + (y / c.ph)) & 1) : 0;
+    return blend_px(p, c.bg[sel][0], c.bg[sel][1], c.bg[sel][2]);
+}
+
 // per-stage launchers (defined in the .cu files); all device pointers
 int launch_compose(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_frames, int has_bg,
                    uint32_t bg, uint32_t pattern, int pw, int ph, int start_row);
@@ -169,8 +204,9 @@ int launch_has_transparency(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h
 int launch_blocks(b200timg_ctx *ctx, const uint8_t *d_fb, const uint8_t *d_prev, int prev_mode,
                   int w, int h, int n_frames, int flags, int x_indent, char *d_out,
                   size_t out_cap, uint64_t *d_offsets);
+// cs != nullptr fuses AlphaComposeBackground (start_row 0) into the scaler's epilogue.
 int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out,
-                 int ow, int oh, int out_frame_rows, int n_frames);
+                 int ow, int oh, int out_frame_rows, int n_frames, const ComposeSpec *cs = nullptr);
 int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
                  size_t out_cap, uint64_t *d_offsets, int phases);
 int sixel_debug_fetch(b200timg_ctx *ctx, uint32_t *h_palette, uint32_t *h_counts, uint8_t *h_index, size_t index_bytes);

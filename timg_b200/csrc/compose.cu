@@ -13,17 +13,6 @@
 
 namespace b200timg {
 
-__device__ __forceinline__ uint32_t blend_px(uint32_t p, float bgr, float bgg, float bgb) {
-    const uint32_t a8 = p >> 24;
-    if (a8 == 0xffu) return p;
-    const uint32_t r8 = p & 0xff, g8 = (p >> 8) & 0xff, b8 = (p >> 16) & 0xff;
-    const float a = (float)a8, ia = (float)(0xff - a8);
-    const float r = fdiv(fadd(fmul((float)(r8 * r8), a), fmul(bgr, ia)), 255.0f);
-    const float g = fdiv(fadd(fmul((float)(g8 * g8), a), fmul(bgg, ia)), 255.0f);
-    const float b = fdiv(fadd(fmul((float)(b8 * b8), a), fmul(bgb, ia)), 255.0f);
-    return pack_rgba(ungamma(r), ungamma(g), ungamma(b), 0xffu);
-}
-
 struct ComposeParams {
     int w, h, start_px;          // start_px = start_row * w
     long long frame_px;          // w*h

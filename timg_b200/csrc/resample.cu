@@ -23,6 +23,7 @@ struct ResampleParams {
     int h_widest, v_widest, h_sequential;
     const int32_t *h_first, *h_count, *h_lead, *v_first, *v_count;
     const float *h_coeff, *v_coeff;
+    ComposeSpec cs;              // fused AlphaComposeBackground (cs.active == 0: none)
 };
 
 struct Px7 { float c[7]; };
@@ -121,7 +122,7 @@ resample_direct_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
 #pragma unroll
         for (int c = 0; c < 7; ++c) res[c] = fadd(acc[0][c], acc[1][c]);
     }
-    out[((long long)f * P.out_frame_rows + oy) * P.ow + ox] = encode_px(res);
+    out[((long long)f * P.out_frame_rows + oy) * P.ow + ox] = compose_at(P.cs, encode_px(res), ox, oy);
 }
 
 // ---- tiled separable kernel ---------------------------------------------------------------
@@ -294,7 +295,7 @@ resample_tiled_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
                 v[3] = res[q].w; v[4] = res[q].x; v[5] = res[q].y; v[6] = res[q].z;
                 const bool transparent = res[q].w < tiny;
                 v[0] = transparent ? plain[q].x : 0.f; v[1] = transparent ? plain[q].y : 0.f; v[2] = transparent ? plain[q].z : 0.f;
-                out[((long long)f * P.out_frame_rows + oy0 + ty) * P.ow + ox0 + tx] = encode_px(v);
+                out[((long long)f * P.out_frame_rows + oy0 + ty) * P.ow + ox0 + tx] = compose_at(P.cs, encode_px(v), ox0 + tx, oy0 + ty);
             }
         }
     }
@@ -457,7 +458,7 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
                 v[3] = res[q].w; v[4] = res[q].x; v[5] = res[q].y; v[6] = res[q].z;
                 const bool transparent = res[q].w < tiny;
                 v[0] = transparent ? plain[q].x : 0.f; v[1] = transparent ? plain[q].y : 0.f; v[2] = transparent ? plain[q].z : 0.f;
-                out[((long long)f * P.out_frame_rows + oy) * P.ow + ox0 + tx] = encode_px(v);
+                out[((long long)f * P.out_frame_rows + oy) * P.ow + ox0 + tx] = compose_at(P.cs, encode_px(v), ox0 + tx, oy);
             }
         }
     }
@@ -516,7 +517,7 @@ resample_copy_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out
         const int oy = (int)(i / P.ow), ox = (int)(i - (long long)oy * P.ow);
         uint32_t p = in[(long long)f * P.iw * P.ih + (long long)P.v_first[oy] * P.iw + P.h_first[ox]];
         if (P.bgra) p = (p & 0xff00ff00u) | ((p & 0xff) << 16) | ((p >> 16) & 0xff);
-        out[((long long)f * P.out_frame_rows + oy) * P.ow + ox] = p;
+        out[((long long)f * P.out_frame_rows + oy) * P.ow + ox] = compose_at(P.cs, p, ox, oy);
     }
 }
 
@@ -524,7 +525,7 @@ resample_copy_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out,
-                 int ow, int oh, int out_frame_rows, int n_frames) {
+                 int ow, int oh, int out_frame_rows, int n_frames, const ComposeSpec *cs) {
     if (out_frame_rows < oh) return ctx->fail(B200TIMG_EINVAL, "scale: frame rows < out height");
     if ((reinterpret_cast<uintptr_t>(d_in) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 3))
         return ctx->fail(B200TIMG_EINVAL, "scale: pixel buffers must be 4-byte aligned");
@@ -562,6 +563,7 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
     ResampleParams P;
     P.iw = iw; P.ih = ih; P.ow = ow; P.oh = oh; P.out_frame_rows = out_frame_rows; P.n_frames = n_frames;
     P.bgra = fmt == B200TIMG_FMT_RGB32;
+    if (cs) P.cs = *cs; else { memset(&P.cs, 0, sizeof P.cs); P.cs.pw = P.cs.ph = 1; }
     P.h_widest = pl->h.widest; P.v_widest = pl->v.widest; P.h_sequential = pl->h_sequential ? 1 : 0;
     P.h_first = reinterpret_cast<const int32_t *>(t + o_hf);
     P.h_count = reinterpret_cast<const int32_t *>(t + o_hc);

@@ -72,9 +72,12 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*
 
 constexpr int PT = 1024;   // palette kernel threads
 
+// SMEM_TABLES: the two median-cut tables live in shared memory (the histogram aliases the second
+// one: it is dead once the first is compacted); otherwise they are in global memory (L2).
+template <bool SMEM_TABLES>
 __global__ void __launch_bounds__(PT)
 sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W) {
-    extern __shared__ uint32_t s_hist[];               // 16384 words: two u16 counters per word
+    extern __shared__ uint32_t s_hist[];               // 16384 words: two u16 counters per word (then table T)
     __shared__ uint32_t s_w[PT / 32];
     __shared__ int b_ind[256], b_col[256], t_ind[256], t_col[256];
     __shared__ uint32_t b_sum[256], t_sum[256];
@@ -88,7 +91,9 @@ sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W)
     const long long npix = (long long)w * h;
     const uint32_t *frame = fb + (long long)f * npix;
     SixelFrameHdr *hdr = W.hdr + f;
-    uint32_t *E = W.ent_a + (long long)f * W.ent_cap, *T = W.ent_b + (long long)f * W.ent_cap;
+    const int t_words = W.ent_cap > 16384 ? W.ent_cap : 16384;
+    uint32_t *E = SMEM_TABLES ? s_hist + t_words : W.ent_a + (long long)f * W.ent_cap;
+    uint32_t *T = SMEM_TABLES ? s_hist : W.ent_b + (long long)f * W.ent_cap;
 
     // quant.c computeHistogram, QUALITY_LOW: step = length/depth/max_sample*depth (bytes)
     unsigned long long step_px = (unsigned long long)npix / 18383ull;
@@ -698,7 +703,16 @@ sixel_compact_kernel(int w, int h, SixelWork W, const uint64_t *__restrict__ off
     const uint32_t n = W.band_bytes[(long long)f * W.nbands + band];
     const char *src = W.scratch + ((size_t)f * W.nbands + band) * W.band_cap;
     char *dst = out + fbase + boff;
-    for (uint32_t i = tid; i < n; i += 256) dst[i] = src[i];
+    {   // word copy: 4-byte aligned stores, source words realigned with a funnel shift
+        const uint32_t head = min(n, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
+        if ((uint32_t)tid < head) dst[tid] = src[tid];
+        const uint32_t nw = (n - head) >> 2, m = head & 3;                 // src slot is 16-byte aligned
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(src + head - m);
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+        for (uint32_t j = tid; j < nw; j += 256) dw[j] = m ? __funnelshift_r(sw[j], sw[j + 1], 8 * m) : sw[j];
+        const uint32_t done = head + (nw << 2);
+        if (done + tid < n) dst[done + tid] = src[done + tid];           // < 4 tail bytes
+    }
     if (tid == 0) {
         if (band > 0) dst[-1] = '-';                         // DECGNL between bands
         if (band == W.nbands - 1) { out[fbase + hdr->frame_size - 2] = '\033'; out[fbase + hdr->frame_size - 1] = '\\'; }
@@ -771,14 +785,23 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     const size_t emit_smem = sizeof(uint32_t) * (size_t)6 * w;
     if (w > 4095 || emit_smem > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
     if (!attrs_set) {
-        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
         attrs_set = true;
     }
     const dim3 egrid(W.nbands, n_frames);
     if (phases & 1) {
     B2_KERNEL(ctx, "sixel_palette_kernel");
-    sixel_palette_kernel<<<n_frames, PT, 65536, ctx->stream>>>(fb, w, h, W);
+    {
+        const size_t t_words = W.ent_cap > 16384 ? (size_t)W.ent_cap : 16384;
+        const size_t smem_tables = sizeof(uint32_t) * (t_words + (size_t)W.ent_cap);
+        if (smem_tables <= 200 * 1024) {
+            B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+            sixel_palette_kernel<true><<<n_frames, PT, smem_tables, ctx->stream>>>(fb, w, h, W);
+        } else {
+            sixel_palette_kernel<false><<<n_frames, PT, 65536, ctx->stream>>>(fb, w, h, W);
+        }
+    }
     B2_LAUNCH_CHECK(ctx);
     B2_KERNEL(ctx, "sixel_lut_kernel");
     sixel_lut_kernel<<<dim3(128, n_frames), 256, 0, ctx->stream>>>(W);
