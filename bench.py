@@ -228,14 +228,15 @@ def main():
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
     launches0 = ctx.launches
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()              # after the sampler start-up, so no rank times another rank's sleep
     torch.cuda.synchronize(dev)
     e0.record(stream)
     for _ in range(args.steps):
