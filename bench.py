@@ -270,8 +270,14 @@ def main():
         alg_bytes = F * (4 * IW * IH) + total_bytes          # read every source pixel once + write every encoded byte once
         peak, how = peak_hbm()
         achieved = alg_bytes / (ms / n / 1e3) / 1e9
+        traffic = None       # dram__bytes_read+write of that kernel per launch, from the committed ncu capture
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            k = json.load(open(tp))["kernels"].get(dom)
+            if k:
+                traffic = k["dram_bytes_per_frame"] * F
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": how,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": ms / n,
                     "kernel_share_of_chain": (ms / 2) / chain_ms,
                     "chain": {"ms_per_step": chain_ms, "achieved": alg_bytes / (chain_ms / 1e3) / 1e9,
