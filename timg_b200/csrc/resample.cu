@@ -315,29 +315,29 @@ resample_tiled_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
 // reading staged (finite) pixels, which adds +0 and changes nothing.  The staged window is padded
 // accordingly (zeros outside the image), its origin per tile column/row comes from the host.
 struct FixedGeom { int nix, niy; const int32_t *tile_ix0, *tile_iy0; };
-constexpr int FTW = 64, FTH = 16;
+constexpr int FTW = 64;
 
-template <bool VFIRST, int HC, int VC>
-__global__ void __launch_bounds__(RT, 3)
+template <bool VFIRST, int HC, int VC, int TH, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, FixedGeom G) {
     extern __shared__ float4 s_px[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.z;
-    const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * FTH;
+    const int ox0 = blockIdx.x * FTW, oy0 = blockIdx.y * TH;
     const int ix0 = G.tile_ix0[blockIdx.x], iy0 = G.tile_iy0[blockIdx.y];
     const int nix = G.nix, niy = G.niy;
     float4 *Din = s_px;
     float4 *T = s_px + (size_t)niy * nix;
-    int *s_hfirst = reinterpret_cast<int *>(T + (VFIRST ? FTH * nix : niy * FTW));   // [FTW]
-    int *s_vfirst = s_hfirst + FTW;                                                   // [FTH]
-    float *s_hc = reinterpret_cast<float *>(s_vfirst + FTH);                          // [FTW][HC+1]
-    float *s_vc = s_hc + FTW * (HC + 1);                                              // [FTH][VC+1]
+    int *s_hfirst = reinterpret_cast<int *>(T + (VFIRST ? TH * nix : niy * FTW));   // [FTW]
+    int *s_vfirst = s_hfirst + FTW;                                                   // [TH]
+    float *s_hc = reinterpret_cast<float *>(s_vfirst + TH);                          // [FTW][HC+1]
+    float *s_vc = s_hc + FTW * (HC + 1);                                              // [TH][VC+1]
     if (tid < FTW) {
         const int ox = ox0 + tid;
         const bool ok = ox < P.ow;
         s_hfirst[tid] = ok ? P.h_first[ox] - ix0 : 0;
 #pragma unroll
         for (int i = 0; i < HC; ++i) s_hc[tid * (HC + 1) + i] = (ok && i < P.h_widest) ? P.h_coeff[(long long)ox * P.h_widest + i] : 0.0f;
-    } else if (tid < FTW + FTH) {
+    } else if (tid < FTW + TH) {
         const int t = tid - FTW, oy = oy0 + t;
         const bool ok = oy < P.oh;
         s_vfirst[t] = ok ? P.v_first[oy] - iy0 : 0;
@@ -347,19 +347,20 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
     const uint32_t *src = in + (long long)f * P.iw * P.ih;
     const bool hseq = P.h_sequential != 0;
     const float tiny = 7.5231638452626401e-37f;       // 2^-120
-    const int tx = tid & (FTW - 1), tyb = tid >> 6;   // this thread's pixels: column tx, rows tyb + 4q
+    constexpr int NW = NT / 32, RSTEP = NT / FTW, RPT = TH / RSTEP;   // warps, row stride, rows per thread
+    const int tx = tid & (FTW - 1), tyb = tid >> 6;   // this thread's pixels: column tx, rows tyb + RSTEP*q
 
-    float4 res[4], plain[4];
+    float4 res[RPT], plain[RPT];
     bool need_plain = false;
     for (int pass = 0; pass < 2; ++pass) {
         // stage + decode the window once.  All of a thread's global loads (up to 4 rows x 4 column
         // groups) are issued before the first one is consumed, so their latencies overlap.
-        for (int ly0 = 0; ly0 < niy; ly0 += 4 * (RT / 32))
+        for (int ly0 = 0; ly0 < niy; ly0 += 4 * NW)
             for (int lx0 = 0; lx0 < nix; lx0 += 128) {
                 uint32_t pv[4][4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const int ly = ly0 + wid + r * (RT / 32), y = iy0 + ly;
+                    const int ly = ly0 + wid + r * NW, y = iy0 + ly;
                     const uint32_t *row = src + (long long)y * P.iw + ix0;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -369,7 +370,7 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const int ly = ly0 + wid + r * (RT / 32);
+                    const int ly = ly0 + wid + r * NW;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int lx = lx0 + lane + 32 * c;
@@ -378,11 +379,11 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
                 }
             }
         __syncthreads();
-        float4 acc[4];
+        float4 acc[RPT];
         if (VFIRST) {
 #pragma unroll
-            for (int r = 0; r < FTH / (RT / 32); ++r) {
-                const int ty = wid + r * (RT / 32);
+            for (int r = 0; r < TH / NW; ++r) {
+                const int ty = wid + r * NW;
                 float vc[VC];
 #pragma unroll
                 for (int k = 0; k < VC; ++k) vc[k] = s_vc[ty * (VC + 1) + k];
@@ -409,8 +410,8 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
             for (int i = 0; i < HC; ++i) hc[i] = s_hc[tx * (HC + 1) + i];
             const float4 *tbase = T + s_hfirst[tx];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 *row = tbase + (tyb + 4 * q) * nix;
+            for (int q = 0; q < RPT; ++q) {
+                const float4 *row = tbase + (tyb + RSTEP * q) * nix;
                 if (hseq) {
                     float4 a = mul4(row[0], hc[0]);
 #pragma unroll
@@ -428,7 +429,7 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
 #pragma unroll
             for (int i = 0; i < HC; ++i) hc[i] = s_hc[tx * (HC + 1) + i];
             const int hn0 = s_hfirst[tx];
-            for (int ly = tyb; ly < niy; ly += 4) {
+            for (int ly = tyb; ly < niy; ly += RSTEP) {
                 const float4 *row = Din + ly * nix + hn0;
                 float4 r;
                 if (hseq) {
@@ -445,8 +446,8 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
             }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int ty = tyb + 4 * q;
+            for (int q = 0; q < RPT; ++q) {
+                const int ty = tyb + RSTEP * q;
                 const float4 *col = T + s_vfirst[ty] * FTW + tx;
                 const float *vc = s_vc + ty * (VC + 1);
                 float4 a = mul4(col[0], vc[0]);
@@ -456,17 +457,17 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { if (pass == 0) res[q] = acc[q]; else plain[q] = acc[q]; }
+        for (int q = 0; q < RPT; ++q) { if (pass == 0) res[q] = acc[q]; else plain[q] = acc[q]; }
         if (pass == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (ox0 + tx < P.ow && oy0 + tyb + 4 * q < P.oh && res[q].w < tiny) need_plain = true;
+            for (int q = 0; q < RPT; ++q) if (ox0 + tx < P.ow && oy0 + tyb + RSTEP * q < P.oh && res[q].w < tiny) need_plain = true;
             if (!__syncthreads_or(need_plain)) break;
         }
     }
     if (ox0 + tx < P.ow) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int oy = oy0 + tyb + 4 * q;
+        for (int q = 0; q < RPT; ++q) {
+            const int oy = oy0 + tyb + RSTEP * q;
             if (oy < P.oh) {
                 float v[7];
                 v[3] = res[q].w; v[4] = res[q].x; v[5] = res[q].y; v[6] = res[q].z;
@@ -479,22 +480,25 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
 }
 
 typedef void (*FixedFn)(const uint32_t *, uint32_t *, ResampleParams, FixedGeom);
+struct FixedVariant { FixedFn fn; int th, nt; };
+// Tile 64x16, 256 threads, 3 CTAs/SM (80 registers) measured best on B200 among {16x256x3, 16x256x4,
+// 8x128x8, 8x256x4, 16x512x2, 32x512x2} (4.21 / 4.76 / 5.01 / 4.79 / 5.45 / 6.75 ms for 64 C2 frames).
 template <bool VF, int HC>
-static FixedFn fixed_v(int vc) {
+static FixedVariant fixed_v(int vc, char v) {
     switch (vc) {
-    case 2: return resample_fixed_kernel<VF, HC, 2>;
-    case 4: return resample_fixed_kernel<VF, HC, 4>;
-    case 6: return resample_fixed_kernel<VF, HC, 6>;
-    default: return resample_fixed_kernel<VF, HC, 8>;
+    case 2: return {resample_fixed_kernel<VF, HC, 2, 16, 256, 3>, 16, 256};
+    case 4: return {resample_fixed_kernel<VF, HC, 4, 16, 256, 3>, 16, 256};
+    case 6: return {resample_fixed_kernel<VF, HC, 6, 16, 256, 3>, 16, 256};
+    default: return {resample_fixed_kernel<VF, HC, 8, 16, 256, 3>, 16, 256};
     }
 }
 template <bool VF>
-static FixedFn fixed_h(int hc, int vc) {
+static FixedVariant fixed_h(int hc, int vc, char v) {
     switch (hc) {
-    case 2: return fixed_v<VF, 2>(vc);
-    case 4: return fixed_v<VF, 4>(vc);
-    case 6: return fixed_v<VF, 6>(vc);
-    default: return fixed_v<VF, 8>(vc);
+    case 2: return fixed_v<VF, 2>(vc, v);
+    case 4: return fixed_v<VF, 4>(vc, v);
+    case 6: return fixed_v<VF, 6>(vc, v);
+    default: return fixed_v<VF, 8>(vc, v);
     }
 }
 static int fixed_class(int widest) { return widest <= 2 ? 2 : widest <= 4 ? 4 : widest <= 6 ? 6 : 8; }
@@ -598,7 +602,9 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
         // fast path: both axes need <= 8 taps -> fixed-tap kernel on 64x16 tiles
         if (pl->h.widest <= 8 && pl->v.widest <= 8 && !getenv("B200TIMG_NO_FIXED")) {
             const int hc = fixed_class(pl->h.widest), vc = fixed_class(pl->v.widest);
-            const int ntx = (ow + FTW - 1) / FTW, nty = (oh + FTH - 1) / FTH;
+            const FixedVariant fv = pl->vertical_first ? fixed_h<true>(hc, vc, 'A') : fixed_h<false>(hc, vc, 'A');
+            const int FTHv = fv.th;
+            const int ntx = (ow + FTW - 1) / FTW, nty = (oh + FTHv - 1) / FTHv;
             std::vector<int32_t> tix(ntx), tiy(nty);
             int nix = 1, niy = 1;
             for (int j = 0; j < ntx; ++j) {
@@ -608,24 +614,22 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
             }
             for (int j = 0; j < nty; ++j) {
                 int lo = 0x7fffffff, hi = -1;
-                for (int y = j * FTH; y < std::min(oh, (j + 1) * FTH); ++y) { lo = std::min(lo, pl->v.first[y]); hi = std::max(hi, pl->v.first[y] + vc - 1); }
+                for (int y = j * FTHv; y < std::min(oh, (j + 1) * FTHv); ++y) { lo = std::min(lo, pl->v.first[y]); hi = std::max(hi, pl->v.first[y] + vc - 1); }
                 tiy[j] = lo; niy = std::max(niy, hi - lo + 1);
             }
-            const size_t fsmem = sizeof(float4) * ((size_t)nix * niy + (pl->vertical_first ? (size_t)FTH * nix : (size_t)niy * FTW))
-                               + sizeof(int) * (FTW + FTH) + sizeof(float) * ((size_t)FTW * (hc + 1) + (size_t)FTH * (vc + 1));
+            const size_t fsmem = sizeof(float4) * ((size_t)nix * niy + (pl->vertical_first ? (size_t)FTHv * nix : (size_t)niy * FTW))
+                               + sizeof(int) * (FTW + FTHv) + sizeof(float) * ((size_t)FTW * (hc + 1) + (size_t)FTHv * (vc + 1));
             if (fsmem <= 100 * 1024) {
-                // tile origins live behind the tap tables in ctx->misc (re-uploaded per call: a few hundred bytes)
+                // tile origins live behind the flag word in ctx->misc (re-uploaded per call: a few hundred bytes)
                 B2_CUDA(ctx, ctx->misc.reserve(4096 + sizeof(int32_t) * (size_t)(ntx + nty)));
                 int32_t *d_t = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 4096);
-                // re-uploaded per call (a few hundred bytes from pageable memory, stream-ordered)
                 B2_CUDA(ctx, cudaMemcpyAsync(d_t, tix.data(), sizeof(int32_t) * ntx, cudaMemcpyHostToDevice, ctx->stream));
                 B2_CUDA(ctx, cudaMemcpyAsync(d_t + ntx, tiy.data(), sizeof(int32_t) * nty, cudaMemcpyHostToDevice, ctx->stream));
                 FixedGeom FG{nix, niy, d_t, d_t + ntx};
-                FixedFn fn = pl->vertical_first ? fixed_h<true>(hc, vc) : fixed_h<false>(hc, vc);
-                B2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                B2_CUDA(ctx, cudaFuncSetAttribute(fv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                 const dim3 grid(ntx, nty, n_frames);
                 B2_KERNEL(ctx, "resample_fixed_kernel");
-                fn<<<grid, RT, fsmem, ctx->stream>>>(in, out, P, FG);
+                fv.fn<<<grid, fv.nt, fsmem, ctx->stream>>>(in, out, P, FG);
                 B2_LAUNCH_CHECK(ctx);
                 return B200TIMG_OK;
             }
