@@ -283,6 +283,23 @@ def main():
                     "chain": {"ms_per_step": chain_ms, "achieved": alg_bytes / (chain_ms / 1e3) / 1e9,
                               "frac": alg_bytes / (chain_ms / 1e3) / 1e9 / peak}}
 
+    # ---- single-frame latency (BASELINE configs[1] is literally one frame): device-resident, batch of 1
+    latency = None
+    if rank == 0:
+        b1 = timg_b200.Batch.from_buffer_copy(b)
+        b1.n_frames = 1
+        for _ in range(3):
+            L.b200timg_sixel_batch_dev(ctx.h, C.byref(b1), frames.data_ptr(), out.data_ptr(), cap, offs.data_ptr())
+        torch.cuda.synchronize(dev)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for _ in range(5):
+            L.b200timg_sixel_batch_dev(ctx.h, C.byref(b1), frames.data_ptr(), out.data_ptr(), cap, offs.data_ptr())
+        l1.record(stream)
+        torch.cuda.synchronize(dev)
+        latency = {"ms": l0.elapsed_time(l1) / 5, "mpx_s": IW * IH / 1e6 / (l0.elapsed_time(l1) / 5 / 1e3),
+                   "note": "one 4K frame through the whole chain; palette + FS wavefront are one CTA per frame"}
+
     # ---- end to end through the host-buffer ABI call: pinned host frames in, host bytes out
     e2e = None
     if not args.no_e2e:
@@ -354,7 +371,8 @@ def main():
                 "config": dict(config, parallelism=f"frames sharded x{world}, NCCL gather of encoded bytes to rank 0"
                                if world > 1 else "1 GPU"),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "kernels": kernels, "encoded_bytes_per_frame": total_bytes // F}
+                "cpu_baseline": cpu, "kernels": kernels, "encoded_bytes_per_frame": total_bytes // F,
+                "single_frame_latency": latency}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
