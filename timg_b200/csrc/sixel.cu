@@ -139,20 +139,109 @@ sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W)
     }
     __syncthreads();
     for (;;) {
-        if (tid == 0) {
-            int bi = 0; const int nb = s_boxes;
-            while (bi < nb && b_col[bi] < 2) ++bi;
-            s_bi = (nb < 256 && bi < nb) ? bi : -1;
-            s_mn[0] = s_mn[1] = s_mn[2] = 31; s_mx[0] = s_mx[1] = s_mx[2] = 0;
-            s_med = ~0ull;
+        if (wid == 0) {                                  // first box (in sorted order) that still has >= 2 colours
+            const int nb = s_boxes;
+            int first = 1 << 30;
+            for (int j = lane; j < nb; j += 32) if (b_col[j] >= 2) { first = j; break; }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+            if (lane == 0) {
+                s_bi = (nb < 256 && first < nb) ? first : -1;
+                s_mn[0] = s_mn[1] = s_mn[2] = 31; s_mx[0] = s_mx[1] = s_mx[2] = 0;
+                s_med = ~0ull;
+            }
+            s_cnt[lane] = 0; s_run[lane] = 0;
         }
-        if (tid < 32) { s_cnt[tid] = 0; s_run[tid] = 0; }
         __syncthreads();
         const int bi = s_bi;
         if (bi < 0) break;
         const int start = b_ind[bi], size = b_col[bi];
         const uint32_t sm = b_sum[bi];
         uint32_t *B = E + start, *TB = T + start;
+        if (size <= 1024) {
+            // Small box (most of the 255 splits): one warp does the whole split with shuffles, the other
+            // warps wait at a single barrier instead of ~20.  Same arithmetic, same stable order.
+            if (wid == 0) {
+                int mn0 = 31, mn1 = 31, mn2 = 31, mx0 = 0, mx1 = 0, mx2 = 0;
+                for (int i = lane; i < size; i += 32) {
+                    const uint32_t e = B[i];
+                    const int k0 = key5(e, 0), k1 = key5(e, 1), k2 = key5(e, 2);
+                    mn0 = min(mn0, k0); mx0 = max(mx0, k0); mn1 = min(mn1, k1); mx1 = max(mx1, k1); mn2 = min(mn2, k2); mx2 = max(mx2, k2);
+                }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, d)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
+                    mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+                    mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, d)); mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, d));
+                }
+                const double lum[3] = {0.2989, 0.5866, 0.1145};
+                const int spreads[3] = {(mx0 - mn0) << 3, (mx1 - mn1) << 3, (mx2 - mn2) << 3};
+                int plane = 0; double best = 0.0;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) { const double sp = lum[p] * (double)spreads[p]; if (sp > best) { plane = p; best = sp; } }
+                // stable counting sort by the 5-bit key: lane k owns key k's counters (s_cnt / s_run were zeroed above)
+                for (int t0 = 0; t0 < size; t0 += 32) {
+                    const int i = t0 + lane;
+                    const bool valid = i < size;
+                    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+                    if (valid) {
+                        const uint32_t k = key5(B[i], plane);
+                        const uint32_t m = __match_any_sync(vm, k);
+                        if ((m & ((1u << lane) - 1)) == 0) s_cnt[k] += __popc(m);
+                    }
+                    __syncwarp();
+                }
+                {
+                    const uint32_t c = s_cnt[lane]; uint32_t inc = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+                    s_base[lane] = inc - c;
+                }
+                __syncwarp();
+                for (int t0 = 0; t0 < size; t0 += 32) {
+                    const int i = t0 + lane;
+                    const bool valid = i < size;
+                    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+                    uint32_t k = 0, m = 0;
+                    if (valid) {
+                        const uint32_t e = B[i];
+                        k = key5(e, plane);
+                        m = __match_any_sync(vm, k);
+                        TB[s_base[k] + s_run[k] + __popc(m & ((1u << lane) - 1))] = e;
+                    }
+                    __syncwarp();
+                    if (valid && (m & ((1u << lane) - 1)) == 0) s_run[k] += __popc(m);
+                    __syncwarp();
+                }
+                for (int i = lane; i < size; i += 32) B[i] = TB[i];
+                __syncwarp();
+                // median by pixel count
+                const uint32_t half = sm / 2;
+                uint32_t carry = 0; int median = size - 1; uint32_t lower = 0; bool found = false;
+                for (int t0 = 0; t0 < size && !found; t0 += 32) {
+                    const int i = t0 + lane;
+                    const uint32_t c = i < size ? (B[i] & 0xffff) : 0;
+                    uint32_t inc = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+                    const uint32_t before = carry + inc - c;
+                    const uint32_t hit = __ballot_sync(0xffffffffu, i >= 1 && i <= size - 2 && before >= half);
+                    if (hit) {
+                        const int src = __ffs(hit) - 1;
+                        median = t0 + src; lower = __shfl_sync(0xffffffffu, before, src); found = true;
+                    }
+                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (!found) lower = sm - (B[size - 1] & 0xffff);
+                if (lane == 0) {
+                    const int nb = s_boxes;
+                    b_col[bi] = median; b_sum[bi] = lower;
+                    b_ind[nb] = start + median; b_col[nb] = size - median; b_sum[nb] = sm - lower;
+                    s_boxes = nb + 1;
+                }
+            }
+            __syncthreads();
+        } else {
         // findBoxBoundaries
         int mn0 = 31, mn1 = 31, mn2 = 31, mx0 = 0, mx1 = 0, mx2 = 0;
         for (int i = tid; i < size; i += PT) {
@@ -241,13 +330,26 @@ sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W)
             s_boxes = nb + 1;
         }
         __syncthreads();
-        {                                               // qsort(bv, boxes, sumcompare): stable, descending
-            const int nb = s_boxes;
-            if (tid < nb) {
-                const uint32_t me = b_sum[tid]; int r = 0;
-                for (int j = 0; j < nb; ++j) { const uint32_t o = b_sum[j]; r += (o > me) || (o == me && j < tid); }
-                t_ind[r] = b_ind[tid]; t_col[r] = b_col[tid]; t_sum[r] = me;
+        }   // large-box path
+        {
+            // qsort(bv, boxes, sumcompare), stable, descending -- but only two elements changed: box `bi`
+            // (sum shrank) and the new box at the end.  Every untouched box keeps its rank among the
+            // untouched ones, so new positions follow from two block-wide counts.
+            const int nb = s_boxes, ia = s_bi, in_ = nb - 1;
+            const uint32_t sA = b_sum[ia], sN = b_sum[in_];
+            int predA = 0, predN = 0, my_pos = -1;
+            uint32_t me = 0;
+            if (tid < nb && tid != ia && tid != in_) {
+                me = b_sum[tid];
+                my_pos = tid - (tid > ia ? 1 : 0) + (((sA > me) || (sA == me && ia < tid)) ? 1 : 0) + ((sN > me) ? 1 : 0);
+                predA = (me > sA) || (me == sA && tid < ia);
+                predN = me >= sN;
             }
+            const int cntA = __syncthreads_count(predA);
+            const int cntN = __syncthreads_count(predN);
+            if (tid == ia) my_pos = cntA + (sN > sA ? 1 : 0);
+            if (tid == in_) my_pos = cntN + (sA >= sN ? 1 : 0);
+            if (tid < nb) { t_ind[my_pos] = b_ind[tid]; t_col[my_pos] = b_col[tid]; t_sum[my_pos] = b_sum[tid]; }
             __syncthreads();
             if (tid < nb) { b_ind[tid] = t_ind[tid]; b_col[tid] = t_col[tid]; b_sum[tid] = t_sum[tid]; }
             __syncthreads();
