@@ -72,6 +72,16 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*
 
 constexpr int PT = 1024;   // palette kernel threads
 
+// quant.c largestByLuminosity: spreads are in 5-bit key units, colour values are key << 3
+__device__ __forceinline__ int pick_plane(int d0, int d1, int d2) {
+    const double lum[3] = {0.2989, 0.5866, 0.1145};
+    const int spreads[3] = {d0 << 3, d1 << 3, d2 << 3};
+    int plane = 0; double best = 0.0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) { const double sp = lum[p] * (double)spreads[p]; if (sp > best) { plane = p; best = sp; } }
+    return plane;
+}
+
 // SMEM_TABLES: the two median-cut tables live in shared memory (the histogram aliases the second
 // one: it is dead once the first is compacted); otherwise they are in global memory (L2).
 template <bool SMEM_TABLES>
@@ -79,12 +89,13 @@ __global__ void __launch_bounds__(PT)
 sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W) {
     extern __shared__ uint32_t s_hist[];               // 16384 words: two u16 counters per word (then table T)
     __shared__ uint32_t s_w[PT / 32];
-    __shared__ int b_ind[256], b_col[256], t_ind[256], t_col[256];
-    __shared__ uint32_t b_sum[256], t_sum[256];
+    __shared__ int b_ind[256], b_col[256], b_med[256], t_ind[256], t_col[256], t_med[256];   // b_med: cached split (-1: none)
+    __shared__ uint32_t b_sum[256], b_low[256], t_sum[256], t_low[256];
     __shared__ int s_mn[3], s_mx[3];
     __shared__ uint32_t s_cnt[32], s_base[32], s_run[32];
     __shared__ unsigned short s_wh[32][32];
-    __shared__ int s_bi, s_plane, s_boxes;
+    __shared__ uint32_t w_cnt[32][32], w_base[32][32], w_run[32][32];      // per-warp counting-sort scratch
+    __shared__ int s_todo[32], s_ntodo, s_boxes, s_done;
     __shared__ unsigned long long s_med;
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -130,38 +141,125 @@ sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W)
         if (tid == 0) hdr->ncolors = n_ent;
         return;
     }
-    // ---- mediancut()
+    // ---- mediancut().  The reference algorithm is sequential: always split the first box (in
+    // population order) that still holds >= 2 colours, 255 times.  A split only reorders the entries
+    // inside its own box and its outcome (median index, lower population) does not depend on any other
+    // box, so splits are computed speculatively, up to 32 boxes per round with one warp each (block-wide
+    // for boxes > 1024 entries), cached per box, and then consumed by one warp in exactly the
+    // sequential order.  Unused speculative results are harmless (the box is merely left sorted).
     {
-        uint32_t s = 0;
-        for (uint32_t i = tid; i < n_ent; i += PT) s += E[i] & 0xffff;
-        uint32_t total; const uint32_t dummy = block_excl_scan<PT>(s, s_w, total); (void)dummy;
-        if (tid == 0) { b_ind[0] = 0; b_col[0] = (int)n_ent; b_sum[0] = total; s_boxes = 1; }
+        uint32_t sacc = 0;
+        for (uint32_t i = tid; i < n_ent; i += PT) sacc += E[i] & 0xffff;
+        uint32_t total; const uint32_t dummy = block_excl_scan<PT>(sacc, s_w, total); (void)dummy;
+        if (tid == 0) { b_ind[0] = 0; b_col[0] = (int)n_ent; b_sum[0] = total; b_med[0] = -1; s_boxes = 1; s_done = 0; }
     }
-    __syncthreads();
     for (;;) {
-        if (wid == 0) {                                  // first box (in sorted order) that still has >= 2 colours
+        __syncthreads();
+        if (wid == 0) {                                  // up to 32 uncached splittable boxes, in order
             const int nb = s_boxes;
-            int first = 1 << 30;
-            for (int j = lane; j < nb; j += 32) if (b_col[j] >= 2) { first = j; break; }
-#pragma unroll
-            for (int d = 16; d; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
-            if (lane == 0) {
-                s_bi = (nb < 256 && first < nb) ? first : -1;
-                s_mn[0] = s_mn[1] = s_mn[2] = 31; s_mx[0] = s_mx[1] = s_mx[2] = 0;
-                s_med = ~0ull;
+            int count = 0;
+            for (int c0 = 0; c0 < nb; c0 += 32) {
+                const int j = c0 + lane;
+                const bool flag = j < nb && b_col[j] >= 2 && b_med[j] < 0;
+                const uint32_t m = __ballot_sync(0xffffffffu, flag);
+                const int pos = count + __popc(m & ((1u << lane) - 1));
+                if (flag && pos < 32) s_todo[pos] = j;
+                count += __popc(m);
             }
-            s_cnt[lane] = 0; s_run[lane] = 0;
+            if (lane == 0) s_ntodo = min(count, 32);
         }
         __syncthreads();
-        const int bi = s_bi;
-        if (bi < 0) break;
-        const int start = b_ind[bi], size = b_col[bi];
-        const uint32_t sm = b_sum[bi];
-        uint32_t *B = E + start, *TB = T + start;
-        if (size <= 1024) {
-            // Small box (most of the 255 splits): one warp does the whole split with shuffles, the other
-            // warps wait at a single barrier instead of ~20.  Same arithmetic, same stable order.
-            if (wid == 0) {
+        const int ntodo = s_ntodo;
+        // (a) big boxes of this round: block-wide, one after the other
+        for (int t = 0; t < ntodo; ++t) {
+            const int bi = s_todo[t];
+            const int start = b_ind[bi], size = b_col[bi];
+            if (size <= 1024) continue;
+            const uint32_t sm = b_sum[bi];
+            uint32_t *B = E + start, *TB = T + start;
+            if (tid == 0) { s_mn[0] = s_mn[1] = s_mn[2] = 31; s_mx[0] = s_mx[1] = s_mx[2] = 0; s_med = ~0ull; }
+            if (tid < 32) { s_cnt[tid] = 0; s_run[tid] = 0; }
+            __syncthreads();
+            int mn0 = 31, mn1 = 31, mn2 = 31, mx0 = 0, mx1 = 0, mx2 = 0;         // findBoxBoundaries
+            for (int i = tid; i < size; i += PT) {
+                const uint32_t e = B[i];
+                const int k0 = key5(e, 0), k1 = key5(e, 1), k2 = key5(e, 2);
+                mn0 = min(mn0, k0); mx0 = max(mx0, k0); mn1 = min(mn1, k1); mx1 = max(mx1, k1); mn2 = min(mn2, k2); mx2 = max(mx2, k2);
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, d)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
+                mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+                mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, d)); mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, d));
+            }
+            if (lane == 0) {
+                atomicMin(&s_mn[0], mn0); atomicMax(&s_mx[0], mx0); atomicMin(&s_mn[1], mn1); atomicMax(&s_mx[1], mx1);
+                atomicMin(&s_mn[2], mn2); atomicMax(&s_mx[2], mx2);
+            }
+            __syncthreads();
+            const int plane = pick_plane(s_mx[0] - s_mn[0], s_mx[1] - s_mn[1], s_mx[2] - s_mn[2]);
+            for (int i = tid; i < size; i += PT) atomicAdd(&s_cnt[key5(B[i], plane)], 1u);   // stable counting sort
+            __syncthreads();
+            if (tid < 32) {
+                const uint32_t c = s_cnt[tid]; uint32_t inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+                s_base[tid] = inc - c;
+            }
+            for (int t0 = 0; t0 < size; t0 += PT) {
+                s_wh[wid][lane] = 0;
+                __syncthreads();
+                const int i = t0 + tid;
+                const bool valid = i < size;
+                uint32_t e = 0, k = 0, rank = 0;
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                if (valid) {
+                    e = B[i]; k = key5(e, plane);
+                    const uint32_t m = __match_any_sync(vmask, k);
+                    rank = __popc(m & ((1u << lane) - 1));
+                    if (rank == 0) s_wh[wid][k] = (unsigned short)__popc(m);
+                }
+                __syncthreads();
+                if (valid) {
+                    uint32_t pp = s_base[k] + s_run[k] + rank;
+                    for (int w2 = 0; w2 < wid; ++w2) pp += s_wh[w2][k];
+                    TB[pp] = e;
+                }
+                __syncthreads();
+                if (tid < 32) { uint32_t acc = 0; for (int w2 = 0; w2 < 32; ++w2) acc += s_wh[w2][tid]; s_run[tid] += acc; }
+                __syncthreads();
+            }
+            for (int i = tid; i < size; i += PT) B[i] = TB[i];
+            __syncthreads();
+            {   // median by pixel count: smallest i in [1, size-2] with sum(count[0..i)) >= sm/2, else size-1
+                const uint32_t half = sm / 2;
+                uint32_t carry = 0;
+                for (int t0 = 0; t0 < size; t0 += PT) {
+                    const int i = t0 + tid;
+                    const uint32_t c = i < size ? (B[i] & 0xffff) : 0;
+                    uint32_t tot; const uint32_t before = carry + block_excl_scan<PT>(c, s_w, tot);
+                    if (i >= 1 && i <= size - 2 && before >= half) atomicMin(&s_med, ((unsigned long long)i << 32) | before);
+                    carry += tot;
+                    __syncthreads();
+                    if (s_med != ~0ull) break;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                if (s_med != ~0ull) { b_med[bi] = (int)(s_med >> 32); b_low[bi] = (uint32_t)s_med; }
+                else { b_med[bi] = size - 1; b_low[bi] = sm - (B[size - 1] & 0xffff); }
+            }
+            __syncthreads();
+        }
+        // (b) small boxes of this round: one warp each, all at once
+        if (wid < ntodo) {
+            const int bi = s_todo[wid];
+            const int start = b_ind[bi], size = b_col[bi];
+            if (size <= 1024) {
+                const uint32_t sm = b_sum[bi];
+                uint32_t *B = E + start, *TB = T + start;
+                uint32_t *cnt = w_cnt[wid], *base = w_base[wid], *run = w_run[wid];
+                cnt[lane] = 0; run[lane] = 0;
                 int mn0 = 31, mn1 = 31, mn2 = 31, mx0 = 0, mx1 = 0, mx2 = 0;
                 for (int i = lane; i < size; i += 32) {
                     const uint32_t e = B[i];
@@ -174,28 +272,24 @@ sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W)
                     mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
                     mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, d)); mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, d));
                 }
-                const double lum[3] = {0.2989, 0.5866, 0.1145};
-                const int spreads[3] = {(mx0 - mn0) << 3, (mx1 - mn1) << 3, (mx2 - mn2) << 3};
-                int plane = 0; double best = 0.0;
-#pragma unroll
-                for (int p = 0; p < 3; ++p) { const double sp = lum[p] * (double)spreads[p]; if (sp > best) { plane = p; best = sp; } }
-                // stable counting sort by the 5-bit key: lane k owns key k's counters (s_cnt / s_run were zeroed above)
-                for (int t0 = 0; t0 < size; t0 += 32) {
+                const int plane = pick_plane(mx0 - mn0, mx1 - mn1, mx2 - mn2);
+                __syncwarp();
+                for (int t0 = 0; t0 < size; t0 += 32) {            // stable counting sort by the 5-bit key
                     const int i = t0 + lane;
                     const bool valid = i < size;
                     const uint32_t vm = __ballot_sync(0xffffffffu, valid);
                     if (valid) {
                         const uint32_t k = key5(B[i], plane);
                         const uint32_t m = __match_any_sync(vm, k);
-                        if ((m & ((1u << lane) - 1)) == 0) s_cnt[k] += __popc(m);
+                        if ((m & ((1u << lane) - 1)) == 0) cnt[k] += __popc(m);
                     }
                     __syncwarp();
                 }
                 {
-                    const uint32_t c = s_cnt[lane]; uint32_t inc = c;
+                    const uint32_t c = cnt[lane]; uint32_t inc = c;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-                    s_base[lane] = inc - c;
+                    base[lane] = inc - c;
                 }
                 __syncwarp();
                 for (int t0 = 0; t0 < size; t0 += 32) {
@@ -207,15 +301,14 @@ sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W)
                         const uint32_t e = B[i];
                         k = key5(e, plane);
                         m = __match_any_sync(vm, k);
-                        TB[s_base[k] + s_run[k] + __popc(m & ((1u << lane) - 1))] = e;
+                        TB[base[k] + run[k] + __popc(m & ((1u << lane) - 1))] = e;
                     }
                     __syncwarp();
-                    if (valid && (m & ((1u << lane) - 1)) == 0) s_run[k] += __popc(m);
+                    if (valid && (m & ((1u << lane) - 1)) == 0) run[k] += __popc(m);
                     __syncwarp();
                 }
                 for (int i = lane; i < size; i += 32) B[i] = TB[i];
                 __syncwarp();
-                // median by pixel count
                 const uint32_t half = sm / 2;
                 uint32_t carry = 0; int median = size - 1; uint32_t lower = 0; bool found = false;
                 for (int t0 = 0; t0 < size && !found; t0 += 32) {
@@ -233,127 +326,72 @@ sixel_palette_kernel(const uint32_t *__restrict__ fb, int w, int h, SixelWork W)
                     carry += __shfl_sync(0xffffffffu, inc, 31);
                 }
                 if (!found) lower = sm - (B[size - 1] & 0xffff);
+                if (lane == 0) { b_med[bi] = median; b_low[bi] = lower; }
+            }
+        }
+        __syncthreads();
+        // (c) consume cached splits in the sequential order (one warp)
+        if (wid == 0) {
+            int done = 0;
+            for (;;) {
+                const int nb = s_boxes;
+                if (nb >= 256) { done = 1; break; }
+                int first = 1 << 30;
+                for (int j = lane; j < nb; j += 32) if (b_col[j] >= 2) { first = j; break; }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+                if (first >= nb) { done = 1; break; }
+                if (b_med[first] < 0) break;                      // not computed yet: next round
+                const int ia = first, in_ = nb, nb1 = nb + 1;
+                const int start = b_ind[ia], size = b_col[ia], median = b_med[ia];
+                const uint32_t sm = b_sum[ia], lower = b_low[ia];
+                __syncwarp();
                 if (lane == 0) {
-                    const int nb = s_boxes;
-                    b_col[bi] = median; b_sum[bi] = lower;
-                    b_ind[nb] = start + median; b_col[nb] = size - median; b_sum[nb] = sm - lower;
-                    s_boxes = nb + 1;
+                    b_col[ia] = median; b_sum[ia] = lower; b_med[ia] = -1;
+                    b_ind[in_] = start + median; b_col[in_] = size - median; b_sum[in_] = sm - lower; b_med[in_] = -1;
+                    s_boxes = nb1;
                 }
-            }
-            __syncthreads();
-        } else {
-        // findBoxBoundaries
-        int mn0 = 31, mn1 = 31, mn2 = 31, mx0 = 0, mx1 = 0, mx2 = 0;
-        for (int i = tid; i < size; i += PT) {
-            const uint32_t e = B[i];
-            const int k0 = key5(e, 0), k1 = key5(e, 1), k2 = key5(e, 2);
-            mn0 = min(mn0, k0); mx0 = max(mx0, k0); mn1 = min(mn1, k1); mx1 = max(mx1, k1); mn2 = min(mn2, k2); mx2 = max(mx2, k2);
-        }
+                __syncwarp();
+                // stable re-sort by population: only box ia (shrunk) and the new last box moved
+                const uint32_t sA = lower, sN = sm - lower;
+                int cntA = 0, cntN = 0;
+                int my_pos[8];
 #pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, d)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
-            mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, d)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
-            mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, d)); mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, d));
-        }
-        if (lane == 0) {
-            atomicMin(&s_mn[0], mn0); atomicMax(&s_mx[0], mx0); atomicMin(&s_mn[1], mn1); atomicMax(&s_mx[1], mx1);
-            atomicMin(&s_mn[2], mn2); atomicMax(&s_mx[2], mx2);
-        }
-        __syncthreads();
-        if (tid == 0) {                                  // largestByLuminosity (colour values are key << 3)
-            const double lum[3] = {0.2989, 0.5866, 0.1145};
-            int plane = 0; double best = 0.0;
-            for (int p = 0; p < 3; ++p) {
-                const double spread = lum[p] * (double)((s_mx[p] - s_mn[p]) << 3);
-                if (spread > best) { plane = p; best = spread; }
-            }
-            s_plane = plane;
-        }
-        __syncthreads();
-        const int plane = s_plane;
-        // stable counting sort of the box by the 5-bit key of `plane` (qsort + compareplane)
-        for (int i = tid; i < size; i += PT) atomicAdd(&s_cnt[key5(B[i], plane)], 1u);
-        __syncthreads();
-        if (tid < 32) {
-            const uint32_t c = s_cnt[tid]; uint32_t inc = c;
+                for (int c = 0; c < 8; ++c) {
+                    const int j = c * 32 + lane;
+                    bool pa = false, pn = false;
+                    my_pos[c] = -1;
+                    if (j < nb1 && j != ia && j != in_) {
+                        const uint32_t me = b_sum[j];
+                        my_pos[c] = j - (j > ia ? 1 : 0) + (((sA > me) || (sA == me && ia < j)) ? 1 : 0) + ((sN > me) ? 1 : 0);
+                        pa = (me > sA) || (me == sA && j < ia);
+                        pn = me >= sN;
+                    }
+                    cntA += __popc(__ballot_sync(0xffffffffu, pa));
+                    cntN += __popc(__ballot_sync(0xffffffffu, pn));
+                }
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-            s_base[tid] = inc - c;
-        }
-        for (int t0 = 0; t0 < size; t0 += PT) {
-            s_wh[wid][lane] = 0;
-            __syncthreads();
-            const int i = t0 + tid;
-            const bool valid = i < size;
-            uint32_t e = 0, k = 0, rank = 0;
-            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                e = B[i]; k = key5(e, plane);
-                const uint32_t m = __match_any_sync(vmask, k);
-                rank = __popc(m & ((1u << lane) - 1));
-                if (rank == 0) s_wh[wid][k] = (unsigned short)__popc(m);
+                for (int c = 0; c < 8; ++c) {
+                    const int j = c * 32 + lane;
+                    if (j < nb1) {
+                        int pos = my_pos[c];
+                        if (j == ia) pos = cntA + (sN > sA ? 1 : 0);
+                        if (j == in_) pos = cntN + (sA >= sN ? 1 : 0);
+                        t_ind[pos] = b_ind[j]; t_col[pos] = b_col[j]; t_sum[pos] = b_sum[j]; t_med[pos] = b_med[j]; t_low[pos] = b_low[j];
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = c * 32 + lane;
+                    if (j < nb1) { b_ind[j] = t_ind[j]; b_col[j] = t_col[j]; b_sum[j] = t_sum[j]; b_med[j] = t_med[j]; b_low[j] = t_low[j]; }
+                }
+                __syncwarp();
             }
-            __syncthreads();
-            if (valid) {
-                uint32_t p = s_base[k] + s_run[k] + rank;
-                for (int w2 = 0; w2 < wid; ++w2) p += s_wh[w2][k];
-                TB[p] = e;
-            }
-            __syncthreads();
-            if (tid < 32) { uint32_t a = 0; for (int w2 = 0; w2 < 32; ++w2) a += s_wh[w2][tid]; s_run[tid] += a; }
-            __syncthreads();
-        }
-        for (int i = tid; i < size; i += PT) B[i] = TB[i];
-        __syncthreads();
-        // median by pixel count: smallest i in [1, size-2] with sum(count[0..i)) >= sm/2, else size-1
-        {
-            const uint32_t half = sm / 2;
-            uint32_t carry = 0;
-            for (int t0 = 0; t0 < size; t0 += PT) {
-                const int i = t0 + tid;
-                const uint32_t c = i < size ? (B[i] & 0xffff) : 0;
-                uint32_t tot; const uint32_t before = carry + block_excl_scan<PT>(c, s_w, tot);
-                if (i >= 1 && i <= size - 2 && before >= half) atomicMin(&s_med, ((unsigned long long)i << 32) | before);
-                carry += tot;
-                __syncthreads();                         // make the atomicMin visible, keep the exit uniform
-                if (s_med != ~0ull) break;
-            }
+            if (lane == 0) s_done = done;
         }
         __syncthreads();
-        if (tid == 0) {
-            int median; uint32_t lower;
-            if (s_med != ~0ull) { median = (int)(s_med >> 32); lower = (uint32_t)s_med; }
-            else { median = size - 1; lower = sm - (B[size - 1] & 0xffff); }
-            const int nb = s_boxes;
-            b_col[bi] = median; b_sum[bi] = lower;
-            b_ind[nb] = start + median; b_col[nb] = size - median; b_sum[nb] = sm - lower;
-            s_boxes = nb + 1;
-        }
-        __syncthreads();
-        }   // large-box path
-        {
-            // qsort(bv, boxes, sumcompare), stable, descending -- but only two elements changed: box `bi`
-            // (sum shrank) and the new box at the end.  Every untouched box keeps its rank among the
-            // untouched ones, so new positions follow from two block-wide counts.
-            const int nb = s_boxes, ia = s_bi, in_ = nb - 1;
-            const uint32_t sA = b_sum[ia], sN = b_sum[in_];
-            int predA = 0, predN = 0, my_pos = -1;
-            uint32_t me = 0;
-            if (tid < nb && tid != ia && tid != in_) {
-                me = b_sum[tid];
-                my_pos = tid - (tid > ia ? 1 : 0) + (((sA > me) || (sA == me && ia < tid)) ? 1 : 0) + ((sN > me) ? 1 : 0);
-                predA = (me > sA) || (me == sA && tid < ia);
-                predN = me >= sN;
-            }
-            const int cntA = __syncthreads_count(predA);
-            const int cntN = __syncthreads_count(predN);
-            if (tid == ia) my_pos = cntA + (sN > sA ? 1 : 0);
-            if (tid == in_) my_pos = cntN + (sA >= sN ? 1 : 0);
-            if (tid < nb) { t_ind[my_pos] = b_ind[tid]; t_col[my_pos] = b_col[tid]; t_sum[my_pos] = b_sum[tid]; }
-            __syncthreads();
-            if (tid < nb) { b_ind[tid] = t_ind[tid]; b_col[tid] = t_col[tid]; b_sum[tid] = t_sum[tid]; }
-            __syncthreads();
-        }
+        if (s_done) break;
     }
     // colormapFromBv, SIXEL_REP_AVERAGE_COLORS: plain mean of the box's colour values
     if (tid < 256) {
