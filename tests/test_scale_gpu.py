@@ -56,3 +56,50 @@ def test_scale_cuda_config_geometries_full_size(ctx):
 def test_identity_scale_is_copy(ctx):
     img = synth.frame_np(5, 333, 77, "noisea")
     assert (ctx.scale(img, 333, 77) == img).all()
+
+
+def _vfirst_small_taps(iw, ih, ow, oh):
+    import timg_b200
+    h, v = timg_b200.resample_plan(iw, ih, ow, oh, 0), timg_b200.resample_plan(iw, ih, ow, oh, 1)
+    return bool(h["flags"] & 1) and not (h["flags"] & 2) and h["widest"] <= 8 and v["widest"] <= 8
+
+
+def test_scale_cuda_planar_path(ctx):
+    """The planar kernel (vertical pass first, <= 8 taps, width % 4 == 0): opaque windows (3 colour
+    planes + analytic alpha), windows with partial alpha (weighted planes + alpha plane), windows with
+    fully transparent output pixels (un-weighted planes too), tiles mixing all three; both byte orders."""
+    rng = np.random.default_rng(77)
+    geoms = [(640, 360, 450, 253), (256, 200, 300, 260), (512, 300, 333, 299), (400, 240, 399, 200),
+             (1024, 64, 720, 45), (64, 1000, 45, 703), (344, 331, 282, 274), (160, 496, 141, 266),
+             (648, 257, 357, 132), (416, 451, 416, 280), (412, 190, 775, 190), (232, 399, 456, 515),
+             (308, 379, 618, 335), (260, 137, 804, 73), (32, 222, 608, 513)]
+    ran_planar = 0
+    for it, (iw, ih, ow, oh) in enumerate(geoms):
+        for kind in ("photo", "noise", "noisea", "alpha", "holes"):
+            if kind == "holes":                       # opaque photo with fully transparent and faint patches
+                img = synth.frame_np(40 + it, iw, ih, "photo")
+                for _ in range(6):
+                    x0, y0 = int(rng.integers(0, iw)), int(rng.integers(0, ih))
+                    img[y0:y0 + int(rng.integers(1, 60)), x0:x0 + int(rng.integers(1, 60)), 3] = int(rng.choice([0, 0, 1, 200]))
+            else:
+                img = synth.frame_np(40 + it, iw, ih, kind)
+            fmt = it % 2
+            ctx.profile(True)
+            got = ctx.scale(img, ow, oh, fmt)
+            rep = ctx.profile_report()
+            ctx.profile(False)
+            want = oracle.stb_resize(img, ow, oh, fmt)
+            assert (got == want).all(), (iw, ih, ow, oh, kind, fmt, int(np.abs(got.astype(int) - want).max()))
+            if "resample_planar_kernel" in rep:
+                assert _vfirst_small_taps(iw, ih, ow, oh)
+                ran_planar += 1
+    assert ran_planar >= 50 or os.environ.get("B200TIMG_NO_PLANAR"), ran_planar
+
+
+def test_scale_cuda_planar_off_matches(ctx, monkeypatch):
+    """Same frame through the planar kernel and through the float4 kernels it replaces."""
+    img = synth.frame_np(9, 640, 360, "alpha")
+    a = ctx.scale(img, 450, 253)
+    monkeypatch.setenv("B200TIMG_NO_PLANAR", "1")
+    b = ctx.scale(img, 450, 253)
+    assert (a == b).all()

@@ -397,7 +397,7 @@ static int batch_host(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t 
     if (!src || !out || !offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
     B2_TRY(pipe_init(ctx));
     const size_t frame_bytes = (size_t)b->src_w * b->src_h * 4;
-    int chunk = (int)std::max<size_t>(1, ((size_t)384 << 20) / frame_bytes);
+    int chunk = (int)std::max<size_t>(1, ((size_t)672 << 20) / frame_bytes);
     if (const char *e = getenv("B200TIMG_CHUNK_FRAMES")) chunk = std::max(1, atoi(e));      // test knob
     if (!sixel && b->animation) chunk = b->n_frames;          // delta frames chain through the whole batch
     chunk = std::min(chunk, b->n_frames);

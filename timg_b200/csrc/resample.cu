@@ -10,6 +10,7 @@
 // working set of a tile stays in L1/L2).  Algorithmic bytes: 4*iw*ih read + 4*ow*oh written.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -479,6 +480,256 @@ resample_fixed_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ ou
     }
 }
 
+// ---- planar fast path (vertical pass first, <= 8 taps per axis) ---------------------------
+// Same arithmetic again, reorganised around what limits resample_fixed_kernel on B200 (shared-memory
+// wavefronts and issue slots, see profiles/): every filtered channel is an independent plane, so the
+// window is staged as separate float planes and
+//   * the vertical pass produces 4 neighbouring columns per thread (one LDS.128 per tap and plane),
+//   * the horizontal pass maps lanes to output ROWS: a warp works on one output column at a time, its
+//     taps and start index are warp-uniform and every tap is one conflict-free wavefront (odd pitch),
+//   * the encoded pixels go through a small transpose buffer so global stores stay coalesced.
+// Channel passes: a tile whose window is fully opaque (the common case: photos, video) needs only the
+// three colour planes -- decoded alpha is exactly 1.0f (255 * fl(1/255) rounds to 1), so R*A == R, and
+// the filtered alpha is the same tap sum over the constant 1.0, computed from the coefficients alone in
+// the same order.  Other tiles run (R*A, G*A, B*A), then A, and -- only if some output alpha is
+// < 2^-120 -- the un-weighted (R, G, B) planes, exactly like the float4 kernels above.
+struct PlanarGeom { int nix, niy, sp, tp; unsigned grp_magic; const int32_t *tile_ix0, *tile_iy0; };   // grp_magic: floor(2^32/(sp/4))+1
+constexpr int PTH = 32;          // output rows per tile (= lanes of the horizontal pass)
+constexpr int PNT = 256;
+
+template <int HC, int VC, int PTW, int MINB>
+__global__ void __launch_bounds__(PNT, MINB)
+resample_planar_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, PlanarGeom G) {
+    extern __shared__ float4 s_px[];
+    float *S = reinterpret_cast<float *>(s_px);                   // [3][niy][sp]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.z;
+    const int ox0 = blockIdx.x * PTW, oy0 = blockIdx.y * PTH;
+    const int ix0 = G.tile_ix0[blockIdx.x], iy0 = G.tile_iy0[blockIdx.y];
+    const int niy = G.niy, sp = G.sp, tp = G.tp;
+    const int splane = niy * sp, tplane = PTH * tp;
+    float *T = S + 3 * splane;                                    // [3][PTH][tp]
+    float *s_hc = T + 3 * tplane + ((4 - ((3 * tplane) & 3)) & 3); // [PTW][8], 16-byte aligned
+    float *s_vc = s_hc + PTW * 8;                                 // [PTH][8]
+    int *s_hfirst = reinterpret_cast<int *>(s_vc + PTH * 8);      // [PTW]
+    int *s_vfirst = s_hfirst + PTW;                               // [PTH]
+    uint32_t *O = reinterpret_cast<uint32_t *>(S);                // [PTH][PTW+1], reuses S after the last pass
+    if (tid < PTW) {
+        const int ox = ox0 + tid;
+        const bool ok = ox < P.ow;
+        s_hfirst[tid] = ok ? P.h_first[ox] - ix0 : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_hc[tid * 8 + i] = (ok && i < P.h_widest) ? P.h_coeff[(long long)ox * P.h_widest + i] : 0.0f;
+    } else if (tid < PTW + PTH) {
+        const int t = tid - PTW, oy = oy0 + t;
+        const bool ok = oy < P.oh;
+        s_vfirst[t] = ok ? P.v_first[oy] - iy0 : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_vc[t * 8 + i] = (ok && i < P.v_widest) ? P.v_coeff[(long long)oy * P.v_widest + i] : 0.0f;
+    }
+    const uint32_t *src = in + (long long)f * P.iw * P.ih;
+    const bool hseq = P.h_sequential != 0;
+    const bool bgra = P.bgra != 0;
+    const float tiny = 7.5231638452626401e-37f;       // 2^-120
+    const float k255 = 1.0f / 255.0f;
+    constexpr int NJ = PTW / 8;                       // output columns per warp: wid + 8*j, row = lane
+    const int ngrp = sp >> 2;                         // 4-column groups per window row
+    const int n_stage = niy * ngrp;
+
+    // ---- staging: a unit is 4 neighbouring source pixels (one 16-byte load) -> one float4 per plane
+    uint4 raw[4];
+    int soff[4];                                      // S offset of the unit, -1: none
+    auto load_chunk = [&](int u0) -> bool {           // all loads of a thread are issued before the first use
+        bool ok255 = true;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int u = u0 + tid + r * PNT;
+            const int ly = (int)__umulhi((unsigned)u, G.grp_magic), g = u - ly * ngrp;
+            const int y = iy0 + ly, x = ix0 + 4 * g;
+            raw[r] = make_uint4(0u, 0u, 0u, 0u);
+            soff[r] = u < n_stage ? ly * sp + 4 * g : -1;
+            if (u < n_stage && y < P.ih && x < P.iw) {
+                raw[r] = __ldg(reinterpret_cast<const uint4 *>(src + (long long)y * P.iw + x));
+                ok255 = ok255 && ((raw[r].x & raw[r].y & raw[r].z & raw[r].w) >= 0xff000000u);
+            }
+        }
+        return ok255;
+    };
+    // mode 0: R*A,G*A,B*A   1: A   2: R,G,B
+    auto decode_chunk = [&](int mode) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (soff[r] < 0) continue;
+            const uint32_t pv[4] = {raw[r].x, raw[r].y, raw[r].z, raw[r].w};
+            float *d = S + soff[r];
+            if (mode == 1) {
+                *reinterpret_cast<float4 *>(d) = make_float4(fmul(byte_f(pv[0], 3), k255), fmul(byte_f(pv[1], 3), k255),
+                                                             fmul(byte_f(pv[2], 3), k255), fmul(byte_f(pv[3], 3), k255));
+                continue;
+            }
+            float c[3][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float c0 = fmul(byte_f(pv[e], 0), k255), c1 = fmul(byte_f(pv[e], 1), k255), c2 = fmul(byte_f(pv[e], 2), k255);
+                c[0][e] = bgra ? c2 : c0; c[1][e] = c1; c[2][e] = bgra ? c0 : c2;
+                if (mode == 0) {
+                    const float a = fmul(byte_f(pv[e], 3), k255);
+                    c[0][e] = fmul(c[0][e], a); c[1][e] = fmul(c[1][e], a); c[2][e] = fmul(c[2][e], a);
+                }
+            }
+            *reinterpret_cast<float4 *>(d) = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
+            *reinterpret_cast<float4 *>(d + splane) = make_float4(c[1][0], c[1][1], c[1][2], c[1][3]);
+            *reinterpret_cast<float4 *>(d + 2 * splane) = make_float4(c[2][0], c[2][1], c[2][2], c[2][3]);
+        }
+    };
+    auto stage = [&](int mode, bool have_first_chunk) {
+        for (int u0 = 0; u0 < n_stage; u0 += 4 * PNT) {
+            if (!(have_first_chunk && u0 == 0)) load_chunk(u0);
+            if (mode == 0) decode_chunk(0); else if (mode == 1) decode_chunk(1); else decode_chunk(2);
+        }
+    };
+    // ---- vertical: T[c][ty][4g..4g+3] = sum_k S[c][vfirst[ty]+k][4g..] * vc[ty][k], rows in order.
+    // A warp covers 4 output rows x 8 column groups: with an odd T pitch its scalar stores hit 32
+    // different banks, and each LDS.128 touches four 128-byte row segments (the minimum).
+    auto vertical = [&](auto np_tag) {
+        constexpr int NP = decltype(np_tag)::value;
+        const int ty = 4 * wid + (lane >> 3);
+        const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + ty * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + ty * 8 + 4);
+        const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const float *sb = S + s_vfirst[ty] * sp + 4 * (lane & 7);
+        float *t = T + ty * tp + 4 * (lane & 7);
+        for (int g = lane & 7; g < ngrp; g += 8, sb += 32, t += 32) {
+#pragma unroll
+            for (int c = 0; c < NP; ++c) {
+                float4 a = mul4(*reinterpret_cast<const float4 *>(sb + c * splane), vc[0]);
+#pragma unroll
+                for (int k = 1; k < VC; ++k) a = add4(a, mul4(*reinterpret_cast<const float4 *>(sb + c * splane + k * sp), vc[k]));
+                float *tc = t + c * tplane;
+                tc[0] = a.x; tc[1] = a.y; tc[2] = a.z; tc[3] = a.w;
+            }
+        }
+    };
+    // tap sum of one output: HC taps alternating between two accumulators (or sequential when <= 3 taps)
+    auto hsum1 = [&](auto tap, const float *hc) -> float {
+        if (hseq) {
+            float a = fmul(tap(0), hc[0]);
+#pragma unroll
+            for (int i = 1; i < (HC < 3 ? HC : 3); ++i) a = fadd(a, fmul(tap(i), hc[i]));
+            return a;
+        }
+        float a0 = fmul(tap(0), hc[0]), a1 = fmul(tap(1), hc[1]);
+#pragma unroll
+        for (int i = 2; i < HC; ++i) { if (i & 1) a1 = fadd(a1, fmul(tap(i), hc[i])); else a0 = fadd(a0, fmul(tap(i), hc[i])); }
+        return fadd(a0, a1);
+    };
+    // ---- horizontal: lane = output row, the warp's column changes with j
+    auto horizontal = [&](auto np_tag, float (*r)[3]) {
+        constexpr int NP = decltype(np_tag)::value;
+        const float *trow = T + lane * tp;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int tx = wid + 8 * j;
+            const float4 h0 = *reinterpret_cast<const float4 *>(s_hc + tx * 8), h1 = *reinterpret_cast<const float4 *>(s_hc + tx * 8 + 4);
+            const float hc[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            const float *row = trow + s_hfirst[tx];
+#pragma unroll
+            for (int c = 0; c < NP; ++c) {
+                const float *rc = row + c * tplane;
+                r[j][c] = hsum1([&](int i) { return rc[i]; }, hc);
+            }
+        }
+    };
+    using I1 = std::integral_constant<int, 1>;
+    using I3 = std::integral_constant<int, 3>;
+
+    float pm[NJ][3], al[NJ], pl[NJ][3];
+    bool have_pl = false;
+    // is every pixel of the window opaque?  (decoded alpha is then exactly 1.0f)
+    bool ok255 = load_chunk(0);
+    for (int u0 = 4 * PNT; u0 < n_stage; u0 += 4 * PNT) ok255 = load_chunk(u0) && ok255;
+    const bool opaque = __syncthreads_and(ok255) != 0;           // also orders the table writes above
+    const bool one_chunk = n_stage <= 4 * PNT;                   // then raw[] still holds the window
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+        // rep 0: weighted colour planes (un-weighted == weighted when opaque); rep 1: un-weighted colour planes
+        if (rep == 0 && !opaque) stage(0, one_chunk); else stage(2, rep == 0 && one_chunk);
+        __syncthreads();
+        vertical(I3());
+        __syncthreads();
+        if (rep == 1) { horizontal(I3(), pl); have_pl = true; break; }
+        horizontal(I3(), pm);
+        if (opaque) {
+            // filtered alpha of an all-ones window: the same two tap sums over the constant 1.0f
+            const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + lane * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + lane * 8 + 4);
+            const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            float av = vc[0];
+#pragma unroll
+            for (int k = 1; k < VC; ++k) av = fadd(av, vc[k]);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int tx = wid + 8 * j;
+                const float4 h0 = *reinterpret_cast<const float4 *>(s_hc + tx * 8), h1 = *reinterpret_cast<const float4 *>(s_hc + tx * 8 + 4);
+                const float hc[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                al[j] = hsum1([&](int) { return av; }, hc);
+            }
+            break;
+        }
+        // alpha plane
+        __syncthreads();                               // T of the colour pass has been consumed
+        stage(1, false);
+        __syncthreads();
+        vertical(I1());
+        __syncthreads();
+        float a1[NJ][3];
+        horizontal(I1(), a1);
+        bool need_plain = false;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            al[j] = a1[j][0];
+            if (ox0 + wid + 8 * j < P.ow && oy0 + lane < P.oh && al[j] < tiny) need_plain = true;
+        }
+        if (!__syncthreads_or(need_plain)) break;
+    }
+    __syncthreads();                                   // every warp is done with S and T
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int tx = wid + 8 * j;
+        float v[7];
+        v[3] = al[j]; v[4] = pm[j][0]; v[5] = pm[j][1]; v[6] = pm[j][2];
+        if (have_pl) { v[0] = pl[j][0]; v[1] = pl[j][1]; v[2] = pl[j][2]; }      // only read when al < 2^-120
+        else { v[0] = pm[j][0]; v[1] = pm[j][1]; v[2] = pm[j][2]; }
+        O[lane * (PTW + 1) + tx] = compose_at(P.cs, encode_px(v), ox0 + tx, oy0 + lane);
+    }
+    __syncthreads();
+    {
+        static_assert(PTW == 32, "store loop maps a lane to a column");
+        uint32_t *orow = out + ((long long)f * P.out_frame_rows + oy0 + wid) * P.ow + ox0 + lane;
+        const bool col_ok = ox0 + lane < P.ow;
+#pragma unroll
+        for (int i = 0; i < PTH / 8; ++i)
+            if (col_ok && oy0 + wid + 8 * i < P.oh) orow[(long long)(8 * i) * P.ow] = O[(wid + 8 * i) * (PTW + 1) + lane];
+    }
+}
+
+typedef void (*PlanarFn)(const uint32_t *, uint32_t *, ResampleParams, PlanarGeom);
+template <int HC, int PTW, int MINB>
+static PlanarFn planar_v(int vc) {
+    switch (vc) {
+    case 2: return resample_planar_kernel<HC, 2, PTW, MINB>;
+    case 4: return resample_planar_kernel<HC, 4, PTW, MINB>;
+    case 6: return resample_planar_kernel<HC, 6, PTW, MINB>;
+    default: return resample_planar_kernel<HC, 8, PTW, MINB>;
+    }
+}
+template <int PTW, int MINB>
+static PlanarFn planar_h(int hc, int vc) {
+    switch (hc) {
+    case 2: return planar_v<2, PTW, MINB>(vc);
+    case 4: return planar_v<4, PTW, MINB>(vc);
+    case 6: return planar_v<6, PTW, MINB>(vc);
+    default: return planar_v<8, PTW, MINB>(vc);
+    }
+}
+
 typedef void (*FixedFn)(const uint32_t *, uint32_t *, ResampleParams, FixedGeom);
 struct FixedVariant { FixedFn fn; int th, nt; };
 // Tile 64x16, 256 threads, 3 CTAs/SM (80 registers) measured best on B200 among {16x256x3, 16x256x4,
@@ -600,6 +851,43 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
     } else {
         if (n_frames > 65535) return ctx->fail(B200TIMG_EINVAL, "scale: too many frames for one launch");
         // fast path: both axes need <= 8 taps -> fixed-tap kernel on 64x16 tiles
+        // fastest path: vertical pass first, <= 8 taps per axis, 16-byte aligned rows -> planar kernel
+        if (pl->vertical_first && pl->h.widest <= 8 && pl->v.widest <= 8 && (iw & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !getenv("B200TIMG_NO_PLANAR") && !getenv("B200TIMG_NO_FIXED")) {
+            const int hc = fixed_class(pl->h.widest), vc = fixed_class(pl->v.widest);
+            const int ptw = 32;
+            const int ntx = (ow + ptw - 1) / ptw, nty = (oh + PTH - 1) / PTH;
+            std::vector<int32_t> tix(ntx), tiy(nty);
+            int nix = 1, niy = 1;
+            for (int j = 0; j < ntx; ++j) {
+                int lo = 0x7fffffff, hi = -1;
+                for (int x = j * ptw; x < std::min(ow, (j + 1) * ptw); ++x) { lo = std::min(lo, pl->h.first[x]); hi = std::max(hi, pl->h.first[x] + hc - 1); }
+                lo &= ~3;                                    // aligned 16-byte loads
+                tix[j] = lo; nix = std::max(nix, hi - lo + 1);
+            }
+            for (int j = 0; j < nty; ++j) {
+                int lo = 0x7fffffff, hi = -1;
+                for (int y = j * PTH; y < std::min(oh, (j + 1) * PTH); ++y) { lo = std::min(lo, pl->v.first[y]); hi = std::max(hi, pl->v.first[y] + vc - 1); }
+                tiy[j] = lo; niy = std::max(niy, hi - lo + 1);
+            }
+            const int sp = (nix + 3) & ~3, tp = sp | 1;   // odd T pitch >= the 4-column groups written per row
+            const size_t psmem = sizeof(float) * (3 * ((size_t)niy * sp + (size_t)PTH * tp) + 4 + (size_t)ptw * 8 + PTH * 8) + sizeof(int) * (ptw + PTH);
+            const size_t smem_cap = 75 * 1024;           // 3 CTAs/SM (80 registers): 7.96 ms vs 10.2 ms at 2 CTAs/SM, 148 C2 frames
+            if (psmem <= smem_cap && (size_t)PTH * (ptw + 1) <= 3 * (size_t)niy * sp) {
+                B2_CUDA(ctx, ctx->misc.reserve(4096 + sizeof(int32_t) * (size_t)(ntx + nty)));
+                int32_t *d_t = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 4096);
+                B2_CUDA(ctx, cudaMemcpyAsync(d_t, tix.data(), sizeof(int32_t) * ntx, cudaMemcpyHostToDevice, ctx->stream));
+                B2_CUDA(ctx, cudaMemcpyAsync(d_t + ntx, tiy.data(), sizeof(int32_t) * nty, cudaMemcpyHostToDevice, ctx->stream));
+                PlanarGeom PG{nix, niy, sp, tp, (unsigned)(0x100000000ull / (unsigned)(sp / 4)) + 1u, d_t, d_t + ntx};
+                PlanarFn fn = planar_h<32, 3>(hc, vc);
+                B2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                const dim3 grid(ntx, nty, n_frames);
+                B2_KERNEL(ctx, "resample_planar_kernel");
+                fn<<<grid, PNT, psmem, ctx->stream>>>(in, out, P, PG);
+                B2_LAUNCH_CHECK(ctx);
+                return B200TIMG_OK;
+            }
+        }
         if (pl->h.widest <= 8 && pl->v.widest <= 8 && !getenv("B200TIMG_NO_FIXED")) {
             const int hc = fixed_class(pl->h.widest), vc = fixed_class(pl->v.widest);
             const FixedVariant fv = pl->vertical_first ? fixed_h<true>(hc, vc, 'A') : fixed_h<false>(hc, vc, 'A');
