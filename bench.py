@@ -206,27 +206,44 @@ def main():
                         bg=timg_b200.rgba_u32(*BG), pattern=0, pattern_w=0, pattern_h=0, flags=0, x_indent_cells=0,
                         animation=0)
     cap = F * 6 * 1024 * 1024
-    out = torch.empty(cap, dtype=torch.uint8, device=dev)
-    offs = torch.zeros(F + 1, dtype=torch.int64, device=dev)
+    # two output buffers: with N > 1 the gather of batch k (NCCL, its own stream) runs while batch k+1 is
+    # being encoded into the other buffer -- the way a stream of pages / video windows would be served
+    nbuf = 2 if world > 1 else 1
+    outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    offss = [torch.zeros(F + 1, dtype=torch.int64, device=dev) for _ in range(nbuf)]
+    out, offs = outs[0], offss[0]
+    pending = [None] * nbuf
+    step_no = [0]
+
+    def drain():
+        for i in range(nbuf):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     def step(gather=True):
-        nonlocal out, cap
-        rc = L.b200timg_sixel_batch_dev(ctx.h, C.byref(b), frames.data_ptr(), out.data_ptr(), cap, offs.data_ptr())
+        i = step_no[0] % nbuf
+        step_no[0] += 1
+        if pending[i] is not None:              # that buffer's previous batch must have left
+            pending[i].wait()
+            pending[i] = None
+        rc = L.b200timg_sixel_batch_dev(ctx.h, C.byref(b), frames.data_ptr(), outs[i].data_ptr(), cap, offss[i].data_ptr())
         if rc != 0:
             raise RuntimeError(L.b200timg_last_error(ctx.h).decode())
         if world > 1 and gather:
-            return shard.gather_encoded(out, offs, dst=0)
-        return None, None
+            pending[i] = shard.gather_encoded_async(outs[i], offss[i], dst=0)
 
-    # first call sizes the output; grow the buffer if the guess was too small (write kernel skips, never overruns)
+    # first call sizes the output; grow the buffers if the guess was too small (write kernel skips, never overruns)
     step(gather=False)
     torch.cuda.synchronize(dev)
-    total = int(offs[-1].item())
+    total = int(offss[0][-1].item())
     if total > cap:
         cap = int(total * 1.05)
-        out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        out = outs[0]
     for _ in range(args.warmup):
         step()
+    drain()
     torch.cuda.synchronize(dev)
     launches0 = ctx.launches
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -241,6 +258,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    drain()                                    # every batch has arrived on rank 0 inside the timed region
     e1.record(stream)
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -252,7 +270,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    total_bytes = int(offs[-1].item())
+    total_bytes = int(offss[0][-1].item())
     value = world * F * args.steps * IW * IH / 1e6 / (ms_total / 1e3)
 
     # ---- per-kernel timing (separate pass, profiling on) -> roofline of the dominant kernel
@@ -368,7 +386,8 @@ def main():
         line = {"metric": "Mpixels/s scale+dither+sixel-encode @4K->cell", "value": value, "unit": "Mpx/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
-                "config": dict(config, parallelism=f"frames sharded x{world}, NCCL gather of encoded bytes to rank 0"
+                "config": dict(config, parallelism=f"frames sharded x{world}, NCCL gather of encoded bytes to rank 0; "
+                               "double-buffered output: the gather of batch k overlaps the kernels of batch k+1"
                                if world > 1 else "1 GPU"),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "kernels": kernels, "encoded_bytes_per_frame": total_bytes // F,

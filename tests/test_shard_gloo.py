@@ -64,3 +64,50 @@ def test_two_rank_gather_preserves_frame_order(n_frames):
         p.join(120)
         assert p.exitcode == 0
     assert list(ok) == [1, 1]
+
+
+def _worker_async(rank, world, port, ok):
+    """Two gathers in flight (double-buffered payloads), waited in order: what bench.py does so that
+    the exchange of batch k overlaps the kernels of batch k+1."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        handles, wants = [], []
+        for batch, n_frames in enumerate((7, 4, 5)):
+            lo, hi = shard.shard_range(n_frames, rank, world)
+            blobs = _fake_frames(100 * batch + lo, 100 * batch + hi)
+            payload = torch.frombuffer(bytearray(b"".join(blobs)) or bytearray(1), dtype=torch.uint8)
+            offsets = torch.tensor(np.concatenate([[0], np.cumsum([len(b) for b in blobs])]), dtype=torch.int64)
+            if len(handles) == 2:
+                res = handles.pop(0).wait()
+                _check(res, wants.pop(0), rank, ok)
+            handles.append(shard.gather_encoded_async(payload, offsets, dst=0))
+            wants.append(_fake_frames(100 * batch, 100 * batch + n_frames))
+        while handles:
+            _check(handles.pop(0).wait(), wants.pop(0), rank, ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def _check(res, want, rank, ok):
+    all_bytes, all_offs = res
+    if rank == 0:
+        got = [bytes(all_bytes[int(all_offs[i]): int(all_offs[i + 1])].numpy().tobytes()) for i in range(len(want))]
+        ok[0] += int(got == want and all_offs.numel() == len(want) + 1)
+    else:
+        ok[rank] += int(all_bytes is None)
+
+
+def test_two_rank_async_gathers_in_flight():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ok = mp.Array("i", [0, 0])
+    procs = [mp.Process(target=_worker_async, args=(r, 2, port, ok)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(ok) == [3, 3]

@@ -18,15 +18,33 @@ def shard_range(n_frames, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_encoded(payload, offsets, dst=0, group=None):
-    """payload: uint8 tensor holding this rank's frames back to back; offsets: int64 tensor [n+1]
-    (same device as payload).  Returns on `dst`: (all_bytes uint8 tensor, all_offsets int64 [N+1])
-    with every rank's frames in rank order; on other ranks (None, None).
+class _Gather:
+    """An in-flight gather_encoded_async: wait() finishes it (on NCCL that makes the *current CUDA
+    stream* wait, not the host) and returns what gather_encoded returns."""
 
-    One size exchange (all_gather of [frame count, byte total]), then point-to-point sends of exactly
-    the encoded bytes and offsets straight into their final place on `dst` (no padding, no concat):
-    payloads are ~4 MB/frame against 33 MB/frame of input, so the link is idle either way and what
-    matters is the number of host round trips."""
+    def __init__(self, works, result, fix, keep=()):
+        self._works, self._result, self._fix, self._keep = works, result, fix, keep   # keep: buffers in flight
+
+    def wait(self):
+        for w in self._works:
+            w.wait()
+        for fs, base in self._fix:
+            if base:
+                fs += base
+        self._works, self._fix, self._keep = [], [], ()
+        return self._result
+
+
+def gather_encoded_async(payload, offsets, dst=0, group=None):
+    """Start gathering this rank's encoded frames to `dst`; returns a handle whose wait() yields, on
+    `dst`, (all_bytes uint8 tensor, all_offsets int64 [N+1]) with every rank's frames in rank order,
+    and (None, None) elsewhere.  `payload` (uint8, frames back to back) and `offsets` (int64 [n+1], same
+    device) must stay untouched until wait() -- callers that keep encoding meanwhile double-buffer them,
+    which is how a stream of pages / video windows hides the exchange behind the next batch's kernels.
+
+    One size exchange (all_gather of [frame count, byte total], the only host sync), then
+    point-to-point sends of exactly the encoded bytes and offsets straight into their final place on
+    `dst` (no padding, no concat)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = payload.device
@@ -39,14 +57,12 @@ def gather_encoded(payload, offsets, dst=0, group=None):
     totals = [int(v[1]) for v in m]
     if rank != dst:
         ops = []
+        offs_out = offsets[1: n_local + 1].to(torch.int64).contiguous()
         if totals[rank]:
             ops.append(dist.P2POp(dist.isend, payload[: totals[rank]], dst, group))
         if counts[rank]:
-            ops.append(dist.P2POp(dist.isend, offsets[1: n_local + 1].to(torch.int64).contiguous(), dst, group))
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        return None, None
+            ops.append(dist.P2POp(dist.isend, offs_out, dst, group))
+        return _Gather(dist.batch_isend_irecv(ops) if ops else [], (None, None), [], (payload, offs_out))
     all_bytes = torch.empty(sum(totals), dtype=torch.uint8, device=dev)
     all_offs = torch.zeros(sum(counts) + 1, dtype=torch.int64, device=dev)
     ops, bbase, fbase, fix = [], 0, 0, []
@@ -63,10 +79,9 @@ def gather_encoded(payload, offsets, dst=0, group=None):
         fix.append((fs, bbase))
         bbase += totals[r]
         fbase += counts[r]
-    if ops:
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
-    for fs, base in fix:
-        if base:
-            fs += base
-    return all_bytes, all_offs
+    return _Gather(dist.batch_isend_irecv(ops) if ops else [], (all_bytes, all_offs), fix)
+
+
+def gather_encoded(payload, offsets, dst=0, group=None):
+    """gather_encoded_async(...).wait(): see there."""
+    return gather_encoded_async(payload, offsets, dst, group).wait()
