@@ -47,9 +47,8 @@ __device__ __forceinline__ uint32_t encode_px(const float *e) {
         r = fmul(e[4], ia); g = fmul(e[5], ia); b = fmul(e[6], ia);
     }
     auto enc = [](float v) -> uint32_t {
-        float f = fadd(fmul(v, 255.0f), 0.5f);
-        f = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
-        return __float2uint_rz(f);
+        const float f = fadd(fmul(v, 255.0f), 0.5f);
+        return __float2uint_rz(fminf(fmaxf(f, 0.0f), 255.0f));     // NaN -> 0 either way (cvt.rzi of NaN is 0)
     };
     return pack_rgba(enc(r), enc(g), enc(b), enc(a));
 }
@@ -528,7 +527,7 @@ resample_planar_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
     }
     const uint32_t *src = in + (long long)f * P.iw * P.ih;
     const bool hseq = P.h_sequential != 0;
-    const bool bgra = P.bgra != 0;
+    const int kr = P.bgra ? 2 : 0, kb = P.bgra ? 0 : 2;          // byte index of R and B in the source pixel
     const float tiny = 7.5231638452626401e-37f;       // 2^-120
     const float k255 = 1.0f / 255.0f;
     constexpr int NJ = PTW / 8;                       // output columns per warp: wid + 8*j, row = lane
@@ -569,8 +568,7 @@ resample_planar_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
             float c[3][4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float c0 = fmul(byte_f(pv[e], 0), k255), c1 = fmul(byte_f(pv[e], 1), k255), c2 = fmul(byte_f(pv[e], 2), k255);
-                c[0][e] = bgra ? c2 : c0; c[1][e] = c1; c[2][e] = bgra ? c0 : c2;
+                c[0][e] = fmul(byte_f(pv[e], kr), k255); c[1][e] = fmul(byte_f(pv[e], 1), k255); c[2][e] = fmul(byte_f(pv[e], kb), k255);
                 if (mode == 0) {
                     const float a = fmul(byte_f(pv[e], 3), k255);
                     c[0][e] = fmul(c[0][e], a); c[1][e] = fmul(c[1][e], a); c[2][e] = fmul(c[2][e], a);

@@ -672,25 +672,26 @@ __device__ __forceinline__ uint32_t column_entries(const uint8_t *__restrict__ i
     return valid;
 }
 
-// bytes the entry at sorted position i contributes (0 unless it starts a run); also returns the
-// pieces the writer needs.
-struct RunInfo { uint32_t bytes, gap, len, c, bits; bool first_of_colour; };
-__device__ __forceinline__ RunInfo run_info(const uint32_t *sorted, int i, int n, uint32_t minc) {
-    RunInfo r;
-    const uint32_t e = sorted[i];
-    r.c = e >> 18; r.bits = e & 63;
-    const uint32_t x = (e >> 6) & 4095;
-    const bool has_prev = i > 0 && (sorted[i - 1] >> 18) == r.c;
-    const uint32_t p = has_prev ? sorted[i - 1] : 0;
-    r.first_of_colour = !has_prev;
-    r.bytes = 0; r.gap = 0; r.len = 0;
-    if (has_prev && ((p >> 6) & 4095) == x - 1 && (p & 63) == r.bits) return r;      // continues the previous run
-    uint32_t L = 1;
-    while (i + (int)L < n && sorted[i + L] == e + (L << 6)) ++L;                     // same colour, x+L, same bits
-    r.len = L;
-    r.gap = has_prev ? x - ((p >> 6) & 4095) - 1 : x;
-    r.bytes = rle_len(r.gap) + rle_len(L) + (has_prev ? 0 : 1 + ndig4(r.c) + (r.c != minc ? 1 : 0));
-    return r;
+// Walk the sorted entries [lo, hi) once and call `emit(c, bits, gap, len, first_of_colour)` for every run
+// that STARTS in the range (a run = same colour, consecutive x, same bits; it may extend past hi, and
+// entries at lo that continue a run started before lo belong to their head's owner and are skipped).
+// gap = blank columns between this run and the colour's previous entry (or x for its first entry).
+template <typename F>
+__device__ __forceinline__ void walk_runs(const uint32_t *sorted, int lo, int hi, int n, F emit) {
+    int i = lo;
+    uint32_t prev = 0; bool have_prev = false;          // the entry just before i, in sorted order
+    if (i > 0 && i < hi) { prev = sorted[i - 1]; have_prev = true; }
+    while (i < hi) {
+        const uint32_t e = sorted[i];
+        if (have_prev && e == prev + 64u) { prev = e; ++i; continue; }        // continues a run: x+1, same colour and bits
+        uint32_t cur = e, L = 1;
+        while (i + (int)L < n && sorted[i + L] == cur + 64u) { cur += 64u; ++L; }
+        const uint32_t c = e >> 18, x = (e >> 6) & 4095u;
+        const bool same_colour = have_prev && (prev >> 18) == c;
+        emit(c, e & 63u, same_colour ? x - ((prev >> 6) & 4095u) - 1u : x, L, !same_colour);
+        prev = cur; have_prev = true;
+        i += (int)L;
+    }
 }
 
 // One CTA per 6-row band.  (1) per-warp counting sort of the band's (colour, x, bits) entries by
@@ -760,18 +761,18 @@ sixel_emit_kernel(EmitGeom G, SixelWork W) {
     const uint32_t minc = s_sorted[0] >> 18;
     const int per = (n + ET - 1) / ET, lo = min(n, tid * per), hi = min(n, lo + per);
     uint32_t local = 0;
-    for (int i = lo; i < hi; ++i) local += run_info(s_sorted, i, n, minc).bytes;
+    walk_runs(s_sorted, lo, hi, n, [&](uint32_t c, uint32_t, uint32_t gap, uint32_t len, bool first) {
+        local += rle_len(gap) + rle_len(len) + (first ? 1u + ndig4(c) + (c != minc ? 1u : 0u) : 0u);
+    });
     uint32_t band_total; uint32_t at = block_excl_scan<ET>(local, s_w, band_total);
     if (tid == 0) W.band_bytes[(long long)f * W.nbands + band] = band_total;
     // (3) bytes, into this band's scratch slot (compacted into the final stream later)
     char *o = W.scratch + ((size_t)f * W.nbands + band) * W.band_cap + at;
-    for (int i = lo; i < hi; ++i) {
-        const RunInfo r = run_info(s_sorted, i, n, minc);
-        if (!r.bytes) continue;
-        if (r.first_of_colour) { if (r.c != minc) *o++ = '$'; *o++ = '#'; o = put_num4(o, r.c); }
-        o = put_rle(o, r.gap, '?');
-        o = put_rle(o, r.len, (char)('?' + r.bits));
-    }
+    walk_runs(s_sorted, lo, hi, n, [&](uint32_t c, uint32_t bits, uint32_t gap, uint32_t len, bool first) {
+        if (first) { if (c != minc) *o++ = '$'; *o++ = '#'; o = put_num4(o, c); }
+        o = put_rle(o, gap, '?');
+        o = put_rle(o, len, (char)('?' + bits));
+    });
 }
 
 // per frame: header length, band offsets (exclusive, in place), frame size
