@@ -10,7 +10,12 @@ using namespace b200timg;
 
 namespace {
 
-int check_ctx(b200timg_ctx *ctx) { return ctx ? B200TIMG_OK : B200TIMG_EINVAL; }
+// Every entry point starts here: a context belongs to one device, whatever the caller's current one is.
+int check_ctx(b200timg_ctx *ctx) {
+    if (!ctx) return B200TIMG_EINVAL;
+    B2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return B200TIMG_OK;
+}
 
 // Upload helper: pageable or pinned host memory -> device, async on the ctx stream.
 int upload(b200timg_ctx *ctx, void *dst, const void *src, size_t bytes) {
@@ -390,8 +395,19 @@ static int pipe_init(b200timg_ctx *ctx) {
 // uploading and chunk k-1's encoded bytes are downloading (three streams, double-buffered staging).
 // Per chunk the encoded size is known before anything is written (sixel) or bounded (blocks), so
 // the caller's buffer is never overrun and *exactly* the encoded bytes cross PCIe on the way back.
+static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,
+                           size_t out_cap, uint64_t *offsets, bool sixel);
 static int batch_host(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,
                       size_t out_cap, uint64_t *offsets, bool sixel) {
+    const int rc = batch_host_impl(ctx, b, src, out, out_cap, offsets, sixel);
+    if (rc != B200TIMG_OK && ctx && ctx->pipe_ready) {      // nothing may still be reading or writing the caller's buffers
+        cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->d2h_stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *src, char *out,
+                           size_t out_cap, uint64_t *offsets, bool sixel) {
     B2_TRY(check_ctx(ctx));
     B2_TRY(validate_batch(ctx, b));
     if (!src || !out || !offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
@@ -439,7 +455,6 @@ static int batch_host(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t 
         const size_t total = (size_t)h_offs[nf];
         for (int j = 1; j <= nf; ++j) offsets[f0 + j] = base_bytes + h_offs[j];
         if (base_bytes + total > out_cap) {
-            cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->d2h_stream);
             return ctx->fail(B200TIMG_ENOSPC, "batch: need more than %zu bytes (have %zu)", base_bytes + total, out_cap);
         }
         if (sixel) {
