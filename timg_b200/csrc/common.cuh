@@ -86,6 +86,7 @@ struct b200timg_ctx {
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_write[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_prep = nullptr;
     b200timg::DevBuf pipe_in[2], pipe_out[2];
     bool pipe_ready = false;
+    bool sixel_attrs_set = false;            // cudaFuncSetAttribute done for this context's device
 
     int fail(int code, const char *fmt, ...) {
         va_list ap; va_start(ap, fmt);

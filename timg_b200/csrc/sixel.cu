@@ -920,59 +920,57 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     W.band_off = reinterpret_cast<uint32_t *>(base + o_bo); W.scratch = base + o_scr;
     const uint32_t *fb = reinterpret_cast<const uint32_t *>(d_fb);
 
-    static bool attrs_set = false;
     EmitGeom G; G.w = w; G.h = h; G.cols_per_warp = ((w + EW - 1) / EW + 31) / 32 * 32;
     const size_t smem_limit = 227 * 1024 - 36 * 1024;   // the emit kernel also has ~33 KB of static shared memory
     const size_t emit_smem = sizeof(uint32_t) * (size_t)6 * w;
     if (w > 4095 || emit_smem > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
-    if (!attrs_set) {
+    if (!ctx->sixel_attrs_set) {                         // function attributes are per device, i.e. per context
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
-        attrs_set = true;
+        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + DW_MAX * DWARP_SMEM));
+        ctx->sixel_attrs_set = true;
     }
     const dim3 egrid(W.nbands, n_frames);
     if (phases & 1) {
-    B2_KERNEL(ctx, "sixel_palette_kernel");
-    {
-        const size_t t_words = W.ent_cap > 16384 ? (size_t)W.ent_cap : 16384;
-        const size_t smem_tables = sizeof(uint32_t) * (t_words + (size_t)W.ent_cap);
-        if (smem_tables <= 200 * 1024) {
-            B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
-            sixel_palette_kernel<true><<<n_frames, PT, smem_tables, ctx->stream>>>(fb, w, h, W);
-        } else {
-            sixel_palette_kernel<false><<<n_frames, PT, 65536, ctx->stream>>>(fb, w, h, W);
+        B2_KERNEL(ctx, "sixel_palette_kernel");
+        {
+            const size_t t_words = W.ent_cap > 16384 ? (size_t)W.ent_cap : 16384;
+            const size_t smem_tables = sizeof(uint32_t) * (t_words + (size_t)W.ent_cap);
+            if (smem_tables <= 200 * 1024) {
+                B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+                sixel_palette_kernel<true><<<n_frames, PT, smem_tables, ctx->stream>>>(fb, w, h, W);
+            } else {
+                sixel_palette_kernel<false><<<n_frames, PT, 65536, ctx->stream>>>(fb, w, h, W);
+            }
         }
-    }
-    B2_LAUNCH_CHECK(ctx);
-    B2_KERNEL(ctx, "sixel_lut_kernel");
-    sixel_lut_kernel<<<dim3(128, n_frames), 256, 0, ctx->stream>>>(W);
-    B2_LAUNCH_CHECK(ctx);
-    {
-        long long blocks = (npix + 255) / 256; if (blocks > 64) blocks = 64;
-        B2_KERNEL(ctx, "sixel_map_kernel");
-        sixel_map_kernel<<<dim3((unsigned)blocks, n_frames), 256, 0, ctx->stream>>>(fb, npix, W);
         B2_LAUNCH_CHECK(ctx);
-    }
-    B2_KERNEL(ctx, "sixel_dither_kernel");
-    {
-        // warps per frame: as many as fit, but in full rounds over the 32-row bands
-        const int rounds = (W.nb32 + DW_MAX - 1) / DW_MAX;
-        const int nwarps = (W.nb32 + rounds - 1) / rounds;
-        const size_t dsmem = 32768 + (size_t)nwarps * DWARP_SMEM;
-        static bool dattr = false;
-        if (!dattr) { B2_CUDA(ctx, cudaFuncSetAttribute(sixel_dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + DW_MAX * DWARP_SMEM)); dattr = true; }
-        sixel_dither_kernel<<<n_frames, nwarps * 32, dsmem, ctx->stream>>>(fb, w, h, nwarps, W);
-    }
-    B2_LAUNCH_CHECK(ctx);
-    B2_KERNEL(ctx, "sixel_emit_kernel");
-    sixel_emit_kernel<<<egrid, ET, emit_smem, ctx->stream>>>(G, W);
-    B2_LAUNCH_CHECK(ctx);
-    B2_KERNEL(ctx, "sixel_layout_kernel");
-    sixel_layout_kernel<<<n_frames, 256, 0, ctx->stream>>>(w, h, W);
-    B2_LAUNCH_CHECK(ctx);
-    B2_KERNEL(ctx, "sixel_sizes_to_offsets_kernel");
-    sixel_sizes_to_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(W.hdr, n_frames, d_offsets);
-    B2_LAUNCH_CHECK(ctx);
+        B2_KERNEL(ctx, "sixel_lut_kernel");
+        sixel_lut_kernel<<<dim3(128, n_frames), 256, 0, ctx->stream>>>(W);
+        B2_LAUNCH_CHECK(ctx);
+        {
+            long long blocks = (npix + 255) / 256; if (blocks > 64) blocks = 64;
+            B2_KERNEL(ctx, "sixel_map_kernel");
+            sixel_map_kernel<<<dim3((unsigned)blocks, n_frames), 256, 0, ctx->stream>>>(fb, npix, W);
+            B2_LAUNCH_CHECK(ctx);
+        }
+        B2_KERNEL(ctx, "sixel_dither_kernel");
+        {
+            // warps per frame: as many as fit, but in full rounds over the 32-row bands
+            const int rounds = (W.nb32 + DW_MAX - 1) / DW_MAX;
+            const int nwarps = (W.nb32 + rounds - 1) / rounds;
+            const size_t dsmem = 32768 + (size_t)nwarps * DWARP_SMEM;
+            sixel_dither_kernel<<<n_frames, nwarps * 32, dsmem, ctx->stream>>>(fb, w, h, nwarps, W);
+        }
+        B2_LAUNCH_CHECK(ctx);
+        B2_KERNEL(ctx, "sixel_emit_kernel");
+        sixel_emit_kernel<<<egrid, ET, emit_smem, ctx->stream>>>(G, W);
+        B2_LAUNCH_CHECK(ctx);
+        B2_KERNEL(ctx, "sixel_layout_kernel");
+        sixel_layout_kernel<<<n_frames, 256, 0, ctx->stream>>>(w, h, W);
+        B2_LAUNCH_CHECK(ctx);
+        B2_KERNEL(ctx, "sixel_sizes_to_offsets_kernel");
+        sixel_sizes_to_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(W.hdr, n_frames, d_offsets);
+        B2_LAUNCH_CHECK(ctx);
     }
     if (!(phases & 2)) return B200TIMG_OK;
     B2_KERNEL(ctx, "sixel_compact_kernel");
