@@ -10,6 +10,7 @@
 #include <csignal>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -99,6 +100,44 @@ int main() {
         printf("blocks quarter=%d upper=%d color8=%d : %zu bytes %s\n", quarter, upper, color8, ref.size(), same ? "identical" : "DIFFERENT");
         failures += !same;
         for (Framebuffer *f : frames) delete f;
+    }
+    // ---- B200SixelCanvas: the in-tree part of SixelCanvas::Send (src/sixel-canvas.cc:100-155) around the
+    // library's DCS stream.  The reference's own SixelCanvas cannot be linked (libsixel is not in the tree),
+    // so the expected bytes are assembled from what that function writes: queued prefix (cursor off, cursor
+    // right by x / cell_x_px), the cursor-placement mode string (:66-79), the stream of the frame padded to a
+    // multiple of 6 rows with the pad strip composed by the REFERENCE's AlphaComposeBackground (:109-120),
+    // then "\r" or "\n" (:150).
+    for (int broken = 0; broken < 2; ++broken) {
+        DisplayOptions opts;
+        opts.cell_x_px = 9; opts.cell_y_px = 18;
+        const rgba_t bg = {10, 20, 30, 255};
+        opts.bgcolor_getter = [bg]() { return bg; };
+        opts.bg_pattern_color = rgba_t{70, 80, 90, 255};
+        opts.pattern_size = 1;
+        SixelOptions so;
+        so.known_broken_cursor_placement = broken != 0;
+        const int w = 100, h = 45, hp = 48, x_px = 18;
+        Framebuffer fb(w, h);
+        fill(&fb, 55 + broken, false);
+        std::vector<Framebuffer *> one{&fb};
+        const std::string got = run_canvas<B200SixelCanvas>(one, x_px, so, opts);
+        Framebuffer padded(w, hp);                                    // zero-initialised == transparent
+        padded.AlphaComposeBackground(opts.bgcolor_getter, opts.bg_pattern_color, opts.pattern_size * opts.cell_x_px,
+                                      opts.pattern_size * opts.cell_y_px / 2, h);
+        std::copy(fb.begin(), fb.end(), padded.begin());
+        std::string dcs(b200timg_sixel_bound(w, hp), '\0');
+        size_t n = 0;
+        B200Context::Check(b200timg_sixel_encode(B200Context::Get(), (const uint8_t *)padded.begin(), w, hp, &dcs[0], dcs.size(), &n),
+                           "sixel_encode");
+        dcs.resize(n);
+        const std::string want = std::string("\033[?25l") + "\033[2C" +
+                                 (broken ? "\033[80l\033[?7730l\033[?8452h" : "\033[80h\033[?7730h\033[?8452l") + dcs +
+                                 (broken ? "\n" : "\r") + "\033[?25h";
+        const bool same = got == want;
+        printf("sixel canvas framing broken_cursor=%d : %zu bytes %s\n", broken, got.size(), same ? "identical" : "DIFFERENT");
+        failures += !same;
+        const bool dcs_ok = dcs.size() > 8 && dcs.compare(0, 3, "\033Pq") == 0 && dcs.compare(dcs.size() - 2, 2, "\033\\") == 0;
+        failures += !dcs_ok;
     }
     printf(failures ? "ADAPTER CHECK FAILED (%d)\n" : "ADAPTER CHECK OK (%d failures)\n", failures);
     return failures ? 1 : 0;

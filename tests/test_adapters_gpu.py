@@ -1,7 +1,9 @@
 """C++-level drop-in check on a B200: oracle/_ref/adapter_check links the reference's own objects, the
 adapters of timg_b200/csrc/adapters.h and libb200timg.so, and drives the reference canvases/scaler and
 ours through the SAME interfaces (ImageScaler, TerminalCanvas + BufferedWriteSequencer), comparing the
-bytes that reach the file descriptor."""
+bytes that reach the file descriptor.  The sixel canvas has no linkable reference counterpart (libsixel
+is not in the tree): its in-tree framing (src/sixel-canvas.cc:100-155) is checked byte for byte around the
+library's own DCS stream."""
 import os
 import subprocess
 
