@@ -35,6 +35,9 @@ KIND = "photo"
 SEED = 1234
 
 
+METRIC = "Mpixels/s scale+dither+sixel-encode @4K\u2192cell"     # BASELINE.json "metric", first clause
+
+
 def geometry():
     import timg_b200
     _, ow, oh = timg_b200.calc_fit(IW, IH, TERM_COLS * CELL_X, TERM_ROWS * CELL_Y, CELL_X, CELL_Y)
@@ -170,7 +173,7 @@ def main():
         value, ms, enc = run_cpu(per_step, max(1, args.steps), max(0, min(args.warmup, 1)), threads)
         import oracle
         kind = "port"   # scaler = the reference's own STB code when oracle/_ref is built; sixel = libsixel restatement
-        line = {"impl": "reference", "metric": "Mpixels/s scale+dither+sixel-encode @4K->cell", "value": value,
+        line = {"impl": "reference", "metric": METRIC, "value": value,
                 "unit": "Mpx/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
                 "config": dict(config, frames_per_step=per_step),
@@ -383,7 +386,7 @@ def main():
         print(f"value {value:.0f} Mpx/s  ms/step {ms_total / args.steps:.3f}  " +
               "  ".join(f"{k.replace('sixel_', '').replace('_kernel', '')}={v['ms_per_launch']:.3f}" for k, v in kernels.items()))
     elif rank == 0:
-        line = {"metric": "Mpixels/s scale+dither+sixel-encode @4K->cell", "value": value, "unit": "Mpx/s",
+        line = {"metric": METRIC, "value": value, "unit": "Mpx/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
                 "config": dict(config, parallelism=f"frames sharded x{world}, NCCL gather of encoded bytes to rank 0; "
