@@ -49,3 +49,23 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".cpp")):
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "import oracle" not in txt and "liboracle" not in txt and "libtimg_ref" not in txt, fn
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/b200timg.h is the FFI contract: it must compile as C99 (no C++/torch types), and a C program
+    must link against the library with nothing but the header."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b200timg.h"\n'
+                   'int main(void) { b200timg_fit_opts o; (void)o; return b200timg_version() > 0 && '
+                   'b200timg_blocks_bound(80, 50) > 0 && b200timg_as256(0xff102030u) >= 16 ? 0 : 1; }\n')
+    exe = tmp_path / "hdr"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                        str(src), "-L", os.path.join(root, "timg_b200"), "-lb200timg",
+                        "-Wl,-rpath," + os.path.join(root, "timg_b200"), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0      # host-only entry points: no GPU needed
