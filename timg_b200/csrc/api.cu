@@ -73,7 +73,7 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     ctx->pinned.release(); ctx->pinned_io.release();
     for (int i = 0; i < 2; ++i) { ctx->pipe_in[i].release(); ctx->pipe_out[i].release(); }
     if (ctx->pipe_ready) {
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_write[i]); cudaEventDestroy(ctx->ev_d2h[i]); }
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_write[i]); cudaEventDestroy(ctx->ev_d2h[i]); cudaEventDestroy(ctx->ev_scaled[i]); }
         cudaEventDestroy(ctx->ev_prep);
         cudaStreamDestroy(ctx->copy_stream); cudaStreamDestroy(ctx->d2h_stream);
     }
@@ -289,9 +289,10 @@ int b200timg_scale_rgba(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, in
 // ---- sixel -----------------------------------------------------------------------------
 size_t b200timg_sixel_bound(int w, int h) {
     // our stream: header + <=256 palette definitions; per 6-row band every column has <= 6
-    // (colour, bits) entries of <= 7 bytes amortised ("!nnnn?" gap + char), plus "$#ccc" per colour
-    const size_t bands = (size_t)(h + 5) / 6;
-    return 32 + 256 * 18 + bands * ((size_t)w * 42 + 256 * 5 + 1) + 2;
+    // (colour, bits) entries of <= 8 bytes ("!nnnnn?" gap + char), plus "#ccc" and "$" per colour and
+    // column tile (tiles of <= 4096 columns), plus "-"
+    const size_t bands = (size_t)(h + 5) / 6, tiles = (size_t)(w + 4095) / 4096;
+    return 32 + 256 * 18 + bands * ((size_t)w * 48 + tiles * 256 * 5 + 1) + 2;
 }
 
 int b200timg_sixel_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, char *out, size_t cap,
@@ -299,20 +300,22 @@ int b200timg_sixel_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, ch
     B2_TRY(check_ctx(ctx));
     if (!fb || !size || w <= 0 || h <= 0 || (h % 6) != 0 || (!out && cap))
         return ctx->fail(B200TIMG_EINVAL, "sixel: bad args (height must be a multiple of 6)");
-    const size_t bytes = (size_t)w * h * 4;
+    // one pass: the frame is encoded into a device staging buffer of worst-case size, and exactly the
+    // encoded bytes come back (or ENOSPC with the size needed, nothing copied)
+    const size_t bytes = (size_t)w * h * 4, bound = b200timg_sixel_bound(w, h);
     B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
+    B2_CUDA(ctx, ctx->out_stage.reserve(bound));
     B2_CUDA(ctx, ctx->offsets.reserve(2 * sizeof(uint64_t)));
     B2_CUDA(ctx, ctx->pinned.reserve(64));
     B2_TRY(upload(ctx, ctx->fb_scaled.p, fb, bytes));
-    B2_TRY(launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, nullptr, 0, ctx->offsets.as<uint64_t>(), 1));
+    B2_TRY(launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, ctx->out_stage.as<char>(), bound,
+                        ctx->offsets.as<uint64_t>(), 3));
     B2_TRY(download(ctx, ctx->pinned.p, ctx->offsets.p, 2 * sizeof(uint64_t)));
     B2_TRY(sync(ctx));
     const size_t n = (size_t)ctx->pinned.as<uint64_t>()[1];
     *size = n;
+    if (n > bound) return ctx->fail(B200TIMG_ECUDA, "sixel: encoded size %zu exceeds the bound %zu", n, bound);
     if (n > cap) return ctx->fail(B200TIMG_ENOSPC, "sixel: need %zu bytes, have %zu", n, cap);
-    B2_CUDA(ctx, ctx->out_stage.reserve(n));
-    B2_TRY(launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, ctx->out_stage.as<char>(), n,
-                        ctx->offsets.as<uint64_t>(), 2));
     B2_TRY(download(ctx, out, ctx->out_stage.p, n));
     return sync(ctx);
 }
@@ -339,6 +342,7 @@ int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const 
     uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
     B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, b->out_h, b->n_frames, &cs));
+    if (ctx->ev_after_scale) B2_CUDA(ctx, cudaEventRecord(ctx->ev_after_scale, ctx->stream));
     return launch_blocks(ctx, d_fb, nullptr, b->animation ? 2 : 0, b->out_w, b->out_h, b->n_frames, b->flags,
                          b->x_indent_cells, d_out, out_cap, d_offsets);
 }
@@ -360,6 +364,7 @@ static int sixel_batch_phases(b200timg_ctx *ctx, const b200timg_batch *b, const 
     // canvas' own start_row = height call (src/sixel-canvas.cc:115-118).
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
     B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, hp, b->n_frames, &cs));
+    if (ctx->ev_after_scale) B2_CUDA(ctx, cudaEventRecord(ctx->ev_after_scale, ctx->stream));
     if (hp != b->out_h) {
         B2_CUDA(ctx, cudaMemset2DAsync(d_fb + (size_t)b->out_h * b->out_w * 4, frame_bytes, 0,
                                        (size_t)(hp - b->out_h) * b->out_w * 4, b->n_frames, ctx->stream));
@@ -385,6 +390,7 @@ static int pipe_init(b200timg_ctx *ctx) {
         B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
         B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_write[i], cudaEventDisableTiming));
         B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_scaled[i], cudaEventDisableTiming));
     }
     B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_prep, cudaEventDisableTiming));
     ctx->pipe_ready = true;
@@ -418,7 +424,8 @@ static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uin
     if (!sixel && b->animation) chunk = b->n_frames;          // delta frames chain through the whole batch
     chunk = std::min(chunk, b->n_frames);
     const int n_chunks = (b->n_frames + chunk - 1) / chunk;
-    const size_t blocks_bound = sixel ? 0 : b200timg_blocks_bound(b->out_w, b->out_h) * (size_t)chunk + 64;
+    const size_t blocks_bound = sixel ? b200timg_sixel_bound(b->out_w, round_to_sixel(b->out_h)) * (size_t)chunk
+                                      : b200timg_blocks_bound(b->out_w, b->out_h) * (size_t)chunk + 64;
     for (int i = 0; i < 2 && i < n_chunks; ++i) B2_CUDA(ctx, ctx->pipe_in[i].reserve(frame_bytes * chunk));
     B2_CUDA(ctx, ctx->offsets.reserve((size_t)(chunk + 1) * sizeof(uint64_t)));
     B2_CUDA(ctx, ctx->pinned.reserve((size_t)(chunk + 1) * sizeof(uint64_t)));
@@ -442,12 +449,16 @@ static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uin
         const uint8_t *d_in = ctx->pipe_in[i].as<uint8_t>();
         B2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[i], 0));
         if (k >= 2) B2_CUDA(ctx, cudaEventSynchronize(ctx->ev_d2h[i]));            // pipe_out[i] is free again
-        if (sixel) {
-            B2_TRY(sixel_batch_phases(ctx, &sub, d_in, nullptr, 0, ctx->offsets.as<uint64_t>(), 1));
-        } else {
-            B2_CUDA(ctx, ctx->pipe_out[i].reserve(blocks_bound));
-            B2_TRY(b200timg_blocks_batch_dev(ctx, &sub, d_in, ctx->pipe_out[i].as<char>(), blocks_bound,
-                                             ctx->offsets.as<uint64_t>()));
+        B2_CUDA(ctx, ctx->pipe_out[i].reserve(blocks_bound));
+        ctx->ev_after_scale = ctx->ev_scaled[i];                                   // recorded once pipe_in[i] has been consumed
+        const int rc_k = sixel ? sixel_batch_phases(ctx, &sub, d_in, ctx->pipe_out[i].as<char>(), blocks_bound, ctx->offsets.as<uint64_t>(), 3)
+                               : b200timg_blocks_batch_dev(ctx, &sub, d_in, ctx->pipe_out[i].as<char>(), blocks_bound,
+                                                           ctx->offsets.as<uint64_t>());
+        ctx->ev_after_scale = nullptr;
+        B2_TRY(rc_k);
+        if (k + 2 < n_chunks) {                                                    // refill pipe_in[i] as soon as this chunk's scaler is done
+            B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scaled[i], 0));
+            B2_TRY(upload_chunk(k + 2));
         }
         B2_CUDA(ctx, cudaMemcpyAsync(h_offs, ctx->offsets.p, (size_t)(nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_prep, ctx->stream));
@@ -457,12 +468,8 @@ static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uin
         if (base_bytes + total > out_cap) {
             return ctx->fail(B200TIMG_ENOSPC, "batch: need more than %zu bytes (have %zu)", base_bytes + total, out_cap);
         }
-        if (sixel) {
-            B2_CUDA(ctx, ctx->pipe_out[i].reserve(total));
-            B2_TRY(sixel_batch_phases(ctx, &sub, nullptr, ctx->pipe_out[i].as<char>(), total, ctx->offsets.as<uint64_t>(), 2));
-        }
+        if (total > blocks_bound) return ctx->fail(B200TIMG_ECUDA, "batch: encoded size %zu exceeds the staging bound %zu", total, blocks_bound);
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_write[i], ctx->stream));
-        if (k + 2 < n_chunks) B2_TRY(upload_chunk(k + 2));                         // pipe_in[i] was consumed by this chunk's scale
         B2_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_write[i], 0));
         if (total) B2_CUDA(ctx, cudaMemcpyAsync(out + base_bytes, ctx->pipe_out[i].p, total, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[i], ctx->d2h_stream));

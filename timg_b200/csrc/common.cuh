@@ -83,7 +83,8 @@ struct b200timg_ctx {
     b200timg::HostBuf pinned_io;   // staging for pageable payloads
     // host-batch pipeline: upload of chunk k+1 / download of chunk k-1 overlap the kernels of chunk k
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
-    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_write[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_prep = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_write[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_scaled[2] = {nullptr, nullptr}, ev_prep = nullptr;
+    cudaEvent_t ev_after_scale = nullptr;      // set by the host pipeline: recorded right after the scaler of a batch call
     b200timg::DevBuf pipe_in[2], pipe_out[2];
     bool pipe_ready = false;
     bool sixel_attrs_set = false;            // cudaFuncSetAttribute done for this context's device

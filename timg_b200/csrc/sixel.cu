@@ -26,49 +26,11 @@
 //   sixel_emit_kernel<0/1> 1 CTA per 6-row band: sizes, then bytes (per-colour RLE rows)
 // Algorithmic bytes per frame: 4*W*H read + encoded bytes written; index plane (1 B/px), boundary
 // rows, LUT and tables are intermediates.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "sixel.cuh"
 
 namespace b200timg {
-
-struct SixelFrameHdr {
-    uint32_t ncolors, origcolors, diffuse, header_len;
-    uint32_t frame_size, pad0, pad1, pad2;
-    uint32_t palette[256];             // r | g << 8 | b << 16
-};
-
-struct SixelWork {                     // device pointers into ctx->sixel_work
-    SixelFrameHdr *hdr;                // [n_frames]
-    uint32_t *ent_a, *ent_b;           // [n_frames][ent_cap] median-cut tables (bucket << 16 | count)
-    uint8_t *lut;                      // [n_frames][32768]
-    uint8_t *index;                    // [n_frames][w*h]
-    uint32_t *boundary;                // [n_frames][nb32][w] packed errors of each 32-row band's last row
-    uint32_t *band_bytes;              // [n_frames][nbands]  sizes
-    uint32_t *band_off;                // [n_frames][nbands]  offset of each band's first byte inside its frame
-    char *scratch;                     // [n_frames][nbands][band_cap] band bytes before compaction
-    size_t band_cap;
-    int ent_cap, nb32, nbands;
-};
-
-__device__ __forceinline__ uint32_t hash15(uint32_t px) {   // (r>>3)<<10 | (g>>3)<<5 | (b>>3)
-    return ((px & 0xf8) << 7) | ((px >> 6) & 0x3e0) | ((px >> 19) & 0x1f);
-}
-__device__ __forceinline__ uint32_t key5(uint32_t entry, int plane) { return (entry >> (26 - 5 * plane)) & 31; }
-
-// ------------------------------------------------------------------ block helpers (1024 thr)
-template <int NT>
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*[NT/32]*/, uint32_t &total) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-    if (lane == 31) s_w[wid] = inc;
-    __syncthreads();
-    uint32_t pre = 0, tot = 0;
-    for (int k = 0; k < NT / 32; ++k) { if (k < wid) pre += s_w[k]; tot += s_w[k]; }
-    total = tot;
-    __syncthreads();
-    return pre + inc - v;
-}
 
 constexpr int PT = 1024;   // palette kernel threads
 
@@ -620,13 +582,6 @@ sixel_dither_kernel(const uint32_t *__restrict__ fb, int w, int h, int nwarps, S
 }
 
 // ---- emit ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ndig_u(uint32_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; ++n; } return n; }
-__device__ __forceinline__ char *put_num_u(char *o, uint32_t v) {
-    char tmp[10]; int n = 0;
-    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) *o++ = tmp[--n];
-    return o;
-}
 // Branch-light formatting for values < 10000 (run lengths, gaps and colour numbers are bounded by
 // the frame width <= 4095 and 255): no loops, so lanes of a warp do not serialise on digit counts.
 __device__ __forceinline__ uint32_t ndig4(uint32_t v) { return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u); }
@@ -650,27 +605,6 @@ constexpr int ET = 512, EW = ET / 32;
 __device__ __forceinline__ uint32_t ent_pack(uint32_t c, uint32_t x, uint32_t bits) { return (c << 18) | (x << 6) | bits; }
 
 struct EmitGeom { int w, h, cols_per_warp; };
-
-// The <=6 distinct (colour, bits) pairs of column x of a 6-row band: slot i is valid iff row i is the
-// first row showing its colour (fixed slots, so everything stays in registers).  Returns the valid mask.
-__device__ __forceinline__ uint32_t column_entries(const uint8_t *__restrict__ idx, int w, int x, uint32_t *c, uint32_t *bits) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) c[i] = idx[(long long)i * w + x];
-    uint32_t valid = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        bool seen = false;
-        uint32_t b = 0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            if (j < i && c[j] == c[i]) seen = true;
-            if (j >= i && c[j] == c[i]) b |= 1u << j;
-        }
-        bits[i] = b;
-        if (!seen) valid |= 1u << i;
-    }
-    return valid;
-}
 
 // Walk the sorted entries [lo, hi) once and call `emit(c, bits, gap, len, first_of_colour)` for every run
 // that STARTS in the range (a run = same colour, consecutive x, same bits; it may extend past hi, and
@@ -908,7 +842,11 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     const size_t o_bo = off; off += align_up(sizeof(uint32_t) * (size_t)W.nbands * n_frames, 256);
     // worst case of one band: <= 6 entries per column, <= 7 bytes each ("!nnnn?" + char), "$#ccc" per colour
     W.band_cap = align_up((size_t)w * 42 + 256 * 5 + 16, 256);
-    const size_t o_scr = off; off += W.band_cap * W.nbands * n_frames;
+    const size_t o_scr = off;
+    const bool emit_v1 = getenv("B200TIMG_EMIT_V1") != nullptr;     // round-1 emitter (sizes + scratch + compaction), kept for A/B runs
+    if (emit_v1) off += W.band_cap * W.nbands * n_frames;
+    size_t e_hdr, e_desc, e_ctl;
+    const size_t o_e2 = off; off += sixel_emit_workspace(w, h, n_frames, &e_hdr, &e_desc, &e_ctl);
     if (phases & 1) B2_CUDA(ctx, ctx->sixel_work.reserve(off));
     if (!ctx->sixel_work.p || ctx->sixel_work.cap < off) return ctx->fail(B200TIMG_EINVAL, "sixel: write phase without prepare");
     ctx->sixel_idx_off = o_idx;
@@ -918,12 +856,15 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     W.lut = reinterpret_cast<uint8_t *>(base + o_lut); W.index = reinterpret_cast<uint8_t *>(base + o_idx);
     W.boundary = reinterpret_cast<uint32_t *>(base + o_bnd); W.band_bytes = reinterpret_cast<uint32_t *>(base + o_bb);
     W.band_off = reinterpret_cast<uint32_t *>(base + o_bo); W.scratch = base + o_scr;
+    W.hdr_bytes = base + o_e2 + e_hdr;
+    W.desc = reinterpret_cast<unsigned long long *>(base + o_e2 + e_desc);
+    W.ctl = reinterpret_cast<uint32_t *>(base + o_e2 + e_ctl);
     const uint32_t *fb = reinterpret_cast<const uint32_t *>(d_fb);
 
     EmitGeom G; G.w = w; G.h = h; G.cols_per_warp = ((w + EW - 1) / EW + 31) / 32 * 32;
     const size_t smem_limit = 227 * 1024 - 36 * 1024;   // the emit kernel also has ~33 KB of static shared memory
     const size_t emit_smem = sizeof(uint32_t) * (size_t)6 * w;
-    if (w > 4095 || emit_smem > smem_limit) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
+    if (emit_v1 && (w > 4095 || emit_smem > smem_limit)) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
     if (!ctx->sixel_attrs_set) {                         // function attributes are per device, i.e. per context
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
@@ -962,6 +903,12 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
             sixel_dither_kernel<<<n_frames, nwarps * 32, dsmem, ctx->stream>>>(fb, w, h, nwarps, W);
         }
         B2_LAUNCH_CHECK(ctx);
+    }
+    if (!emit_v1) {
+        if (!(phases & 2)) return B200TIMG_OK;
+        return launch_sixel_emit(ctx, w, h, n_frames, W, d_out, out_cap, d_offsets);
+    }
+    if (phases & 1) {
         B2_KERNEL(ctx, "sixel_emit_kernel");
         sixel_emit_kernel<<<egrid, ET, emit_smem, ctx->stream>>>(G, W);
         B2_LAUNCH_CHECK(ctx);
