@@ -845,6 +845,9 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     const size_t o_scr = off;
     const bool emit_v1 = getenv("B200TIMG_EMIT_V1") != nullptr;     // round-1 emitter (sizes + scratch + compaction), kept for A/B runs
     if (emit_v1) off += W.band_cap * W.nbands * n_frames;
+    const bool dither_v1 = getenv("B200TIMG_DITHER_V1") != nullptr; // round-1 ditherer, kept for A/B runs
+    size_t d_bnd, d_prog;
+    const size_t o_d2 = off; off += sixel_dither_workspace(w, h, n_frames, &d_bnd, &d_prog);
     size_t e_hdr, e_desc, e_ctl;
     const size_t o_e2 = off; off += sixel_emit_workspace(w, h, n_frames, &e_hdr, &e_desc, &e_ctl);
     if (phases & 1) B2_CUDA(ctx, ctx->sixel_work.reserve(off));
@@ -894,6 +897,9 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
             sixel_map_kernel<<<dim3((unsigned)blocks, n_frames), 256, 0, ctx->stream>>>(fb, npix, W);
             B2_LAUNCH_CHECK(ctx);
         }
+        if (!dither_v1) {
+            B2_TRY(launch_sixel_dither(ctx, fb, w, h, n_frames, W, base + o_d2 + d_bnd, base + o_d2 + d_prog));
+        } else {
         B2_KERNEL(ctx, "sixel_dither_kernel");
         {
             // warps per frame: as many as fit, but in full rounds over the 32-row bands
@@ -903,6 +909,7 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
             sixel_dither_kernel<<<n_frames, nwarps * 32, dsmem, ctx->stream>>>(fb, w, h, nwarps, W);
         }
         B2_LAUNCH_CHECK(ctx);
+        }
     }
     if (!emit_v1) {
         if (!(phases & 2)) return B200TIMG_OK;
