@@ -24,11 +24,11 @@ __global__ void __launch_bounds__(256)
 compose_kernel(uint32_t *__restrict__ fb, ComposeParams P, long long total_quads) {
     // one thread = 4 consecutive pixels of one frame (frame_px % 4 == 0 path) or 1 pixel
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long qpf = P.frame_px >> 2;
+    // only the quads at or after start_row are visited (the sixel pad strip is a few rows of each frame)
+    const long long q0 = (long long)(P.start_px >> 2), rq = (P.frame_px >> 2) - q0;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += stride) {
-        const long long f = q / qpf;
-        const long long i0 = (q - f * qpf) << 2;          // pixel index inside frame
-        if (i0 + 3 < P.start_px) continue;
+        const long long f = q / rq;
+        const long long i0 = (q0 + (q - f * rq)) << 2;    // pixel index inside frame
         uint4 *ptr = reinterpret_cast<uint4 *>(fb + f * P.frame_px + i0);
         uint4 v = *ptr;
         if (((v.x & v.y & v.z & v.w) >> 24) == 0xffu) continue;   // all four opaque
@@ -51,10 +51,11 @@ compose_kernel(uint32_t *__restrict__ fb, ComposeParams P, long long total_quads
 __global__ void __launch_bounds__(256)
 compose_kernel_scalar(uint32_t *__restrict__ fb, ComposeParams P, long long total_px) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total_px; g += stride) {
-        const long long f = g / P.frame_px;
-        const long long i = g - f * P.frame_px;
-        if (i < P.start_px) continue;
+    const long long rp = P.frame_px - P.start_px;           // pixels per frame at or after start_row
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total_px; t += stride) {
+        const long long f = t / rp;
+        const long long i = P.start_px + (t - f * rp);
+        const long long g = f * P.frame_px + i;
         const uint32_t p = fb[g];
         if ((p >> 24) == 0xffu) continue;
         int sel = 0;
@@ -96,7 +97,7 @@ int launch_compose(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_frames,
     const bool vec = (P.frame_px % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_fb) & 15) == 0);
     const int threads = 256;
     if (vec) {
-        const long long quads = total_px >> 2;
+        const long long quads = ((P.frame_px >> 2) - (P.start_px >> 2)) * n_frames;
         long long blocks = (quads + threads - 1) / threads;
         const long long cap = (long long)ctx->sm_count * 16;
         if (blocks > cap) blocks = cap;
@@ -105,13 +106,14 @@ int launch_compose(b200timg_ctx *ctx, uint8_t *d_fb, int w, int h, int n_frames,
         compose_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
             reinterpret_cast<uint32_t *>(d_fb), P, quads);
     } else {
-        long long blocks = (total_px + threads - 1) / threads;
+        const long long region_px = (P.frame_px - P.start_px) * n_frames;
+        long long blocks = (region_px + threads - 1) / threads;
         const long long cap = (long long)ctx->sm_count * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
         B2_KERNEL(ctx, "compose_kernel_scalar");
         compose_kernel_scalar<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
-            reinterpret_cast<uint32_t *>(d_fb), P, total_px);
+            reinterpret_cast<uint32_t *>(d_fb), P, region_px);
     }
     B2_LAUNCH_CHECK(ctx);
     return B200TIMG_OK;

@@ -843,7 +843,9 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     // worst case of one band: <= 6 entries per column, <= 7 bytes each ("!nnnn?" + char), "$#ccc" per colour
     W.band_cap = align_up((size_t)w * 42 + 256 * 5 + 16, 256);
     const size_t o_scr = off;
-    const bool emit_v1 = getenv("B200TIMG_EMIT_V1") != nullptr;     // round-1 emitter (sizes + scratch + compaction), kept for A/B runs
+    // two emitters: v1 (per-band sizes into a scratch arena + compaction kernel; <= 4095 px wide) and the single-pass v2
+    // (sixel_emit.cu: any width, no arena).  v2 is used where v1 cannot go and when B200TIMG_EMIT_V2 is set.
+    const bool emit_v1 = !getenv("B200TIMG_EMIT_V2") && w <= 4095 && sizeof(uint32_t) * (size_t)6 * w <= (size_t)(227 - 36) * 1024;
     if (emit_v1) off += W.band_cap * W.nbands * n_frames;
     const bool dither_v1 = getenv("B200TIMG_DITHER_V1") != nullptr; // round-1 ditherer, kept for A/B runs
     size_t d_bnd, d_prog;
