@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernels-only", action="store_true", help="print just the per-kernel table (tuning runs)")
+    ap.add_argument("--exact-scale", action="store_true",
+                    help="bit-exact scaler arithmetic instead of the <= 1 LSB fused-multiply-add mode (B200TIMG_FAST_SCALE)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -206,8 +208,8 @@ def main():
         frames[i] = synth.frame_torch(SEED + rank * F + i, IW, IH, KIND, dev)
     torch.cuda.synchronize(dev)
     b = timg_b200.Batch(n_frames=F, src_w=IW, src_h=IH, src_fmt=0, out_w=ow, out_h=oh, has_bg=1,
-                        bg=timg_b200.rgba_u32(*BG), pattern=0, pattern_w=0, pattern_h=0, flags=0, x_indent_cells=0,
-                        animation=0)
+                        bg=timg_b200.rgba_u32(*BG), pattern=0, pattern_w=0, pattern_h=0,
+                        flags=0 if args.exact_scale else timg_b200.FAST_SCALE, x_indent_cells=0, animation=0)
     cap = F * 6 * 1024 * 1024
     # two output buffers: with N > 1 the gather of batch k (NCCL, its own stream) runs while batch k+1 is
     # being encoded into the other buffer -- the way a stream of pages / video windows would be served

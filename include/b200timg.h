@@ -47,6 +47,11 @@ extern "C" {
 #define B200TIMG_QUARTER   1    /* use_quarter: 2x2 px per cell instead of 1x2 */
 #define B200TIMG_UPPER     2    /* use_upper_half_block (TIMG_USE_UPPER_BLOCK) */
 #define B200TIMG_COLOR8    4    /* use_256_color (--color8) */
+/* batch flag (not a reference option): let the scaler use fused multiply-adds and skip the
+ * byte*(1/255) .. *255 round trip where a kernel offers it.  Result within 1 LSB per channel of
+ * ImageScaler::Scale's instead of bit-identical.  Meant for -p sixel, whose quantiser is compared
+ * by a colour-difference tolerance anyway; never set it for the block modes' byte parity. */
+#define B200TIMG_FAST_SCALE 8
 
 /* input colour formats: ImageScaler::ColorFmt, src/image-scaler.h:26-29 */
 #define B200TIMG_FMT_RGBA  0
@@ -87,6 +92,9 @@ int b200timg_as256(uint32_t rgba);
  * alpha-weighted, per axis.  in: iw*ih*4 bytes, out: ow*oh*4 bytes. */
 int b200timg_scale_rgba(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt,
                         uint8_t *out, int ow, int oh);
+/* Same with fast != 0 selecting the <= 1 LSB arithmetic described at B200TIMG_FAST_SCALE. */
+int b200timg_scale_rgba_mode(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt,
+                             uint8_t *out, int ow, int oh, int fast);
 
 /* Framebuffer::AlphaComposeBackground (src/framebuffer.cc:108-150), in place on fb.
  * has_bg==0 models a null bgcolor_getter ("-b none"); the lazy getter itself stays on

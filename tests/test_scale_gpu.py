@@ -65,7 +65,7 @@ def _vfirst_small_taps(iw, ih, ow, oh):
 
 
 def test_scale_cuda_planar_path(ctx):
-    """The planar kernel (vertical pass first, <= 8 taps, width % 4 == 0): opaque windows (3 colour
+    """The v3 kernel (opaque tiles) + planar kernel (vertical pass first, <= 8 taps, width % 4 == 0): opaque windows (3 colour
     planes + analytic alpha), windows with partial alpha (weighted planes + alpha plane), windows with
     fully transparent output pixels (un-weighted planes too), tiles mixing all three; both byte orders."""
     rng = np.random.default_rng(77)
@@ -90,7 +90,7 @@ def test_scale_cuda_planar_path(ctx):
             ctx.profile(False)
             want = oracle.stb_resize(img, ow, oh, fmt)
             assert (got == want).all(), (iw, ih, ow, oh, kind, fmt, int(np.abs(got.astype(int) - want).max()))
-            if "resample_planar_kernel" in rep:
+            if "resample_planar_kernel" in rep or "resample_v3_exact_kernel" in rep:     # v3 = opaque tiles, planar = the rest
                 assert _vfirst_small_taps(iw, ih, ow, oh)
                 ran_planar += 1
     assert ran_planar >= 50 or os.environ.get("B200TIMG_NO_PLANAR"), ran_planar
@@ -103,3 +103,24 @@ def test_scale_cuda_planar_off_matches(ctx, monkeypatch):
     monkeypatch.setenv("B200TIMG_NO_PLANAR", "1")
     b = ctx.scale(img, 450, 253)
     assert (a == b).all()
+
+
+# B200TIMG_FAST_SCALE: fused multiply-adds, no byte*(1/255) .. *255 round trip.  Stated tolerance (BASELINE.md:
+# "<= 1 LSB for Mitchell vs STB"): every channel within 1 of the reference, and fewer than 0.5 % of the pixels
+# differing at all (measured: <= 0.05 %).
+FAST_MAX_LSB = 1
+FAST_MAX_FRACTION = 0.005
+
+
+@pytest.mark.parametrize("iw,ih,ow,oh,kind", [(128, 96, 90, 67, "photo"), (256, 128, 200, 100, "noise"),
+                                               (3840, 128, 2700, 90, "photo"), (640, 480, 450, 337, "noise"),
+                                               (1024, 64, 720, 45, "photo"), (512, 300, 333, 299, "noisea"),
+                                               (640, 360, 450, 253, "alpha")])
+def test_scale_cuda_fast_mode_within_one_lsb(ctx, iw, ih, ow, oh, kind):
+    img = synth.frame_np(5 + iw, iw, ih, kind)
+    for fmt in (0, 1):
+        want = oracle.stb_resize(img, ow, oh, fmt)
+        got = ctx.scale(img, ow, oh, fmt, fast=True)
+        d = np.abs(got.astype(int) - want)
+        assert d.max() <= FAST_MAX_LSB, (iw, ih, ow, oh, kind, fmt, int(d.max()))
+        assert (d.max(-1) > 0).mean() < FAST_MAX_FRACTION

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200timg.so")
 
 OK, EINVAL, ENOMEM, ECUDA, ENOSPC, ENODEV = 0, -1, -2, -3, -4, -5
-QUARTER, UPPER, COLOR8 = 1, 2, 4
+QUARTER, UPPER, COLOR8, FAST_SCALE = 1, 2, 4, 8
 FMT_RGBA, FMT_RGB32 = 0, 1
 
 u8p = C.POINTER(C.c_uint8)
@@ -47,6 +47,7 @@ ABI = {
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b200timg_as256": (C.c_int, [C.c_uint32]),
     "b200timg_scale_rgba": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]),
+    "b200timg_scale_rgba_mode": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int]),
     "b200timg_compose_bg": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
                                       C.c_int, C.c_int, C.c_int]),
     "b200timg_has_transparency": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
@@ -172,11 +173,11 @@ class Context:
         return lib().b200timg_kernel_launches(self.h)
 
     # ---- single-frame host entry points (numpy in / numpy or bytes out)
-    def scale(self, img, ow, oh, fmt=FMT_RGBA):
+    def scale(self, img, ow, oh, fmt=FMT_RGBA, fast=False):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         ih, iw = img.shape[:2]
         out = np.empty((oh, ow, 4), np.uint8)
-        self._chk(lib().b200timg_scale_rgba(self.h, _np_ptr(img), iw, ih, fmt, _np_ptr(out), ow, oh))
+        self._chk(lib().b200timg_scale_rgba_mode(self.h, _np_ptr(img), iw, ih, fmt, _np_ptr(out), ow, oh, int(fast)))
         return out
 
     def compose_bg(self, fb, bg, pattern=0, pw=0, ph=0, start_row=0, has_bg=True):

@@ -69,7 +69,7 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->in_stage.release(); ctx->fb_scaled.release(); ctx->prev_stage.release();
     ctx->out_stage.release(); ctx->offsets.release(); ctx->cells.release(); ctx->rows.release();
-    ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release();
+    ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release(); ctx->scale_list.release();
     ctx->pinned.release(); ctx->pinned_io.release();
     for (int i = 0; i < 2; ++i) { ctx->pipe_in[i].release(); ctx->pipe_out[i].release(); }
     if (ctx->pipe_ready) {
@@ -275,13 +275,18 @@ int b200timg_scale_dev(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, i
 
 int b200timg_scale_rgba(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt, uint8_t *out,
                         int ow, int oh) {
+    return b200timg_scale_rgba_mode(ctx, in, iw, ih, fmt, out, ow, oh, 0);
+}
+
+int b200timg_scale_rgba_mode(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt, uint8_t *out,
+                             int ow, int oh, int fast) {
     B2_TRY(check_ctx(ctx));
     if (!in || !out || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return ctx->fail(B200TIMG_EINVAL, "scale: bad args");
     const size_t ib = (size_t)iw * ih * 4, ob = (size_t)ow * oh * 4;
     B2_CUDA(ctx, ctx->in_stage.reserve(ib));
     B2_CUDA(ctx, ctx->fb_scaled.reserve(ob));
     B2_TRY(upload(ctx, ctx->in_stage.p, in, ib));
-    B2_TRY(launch_scale(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1));
+    B2_TRY(launch_scale(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1, nullptr, fast));
     B2_TRY(download(ctx, out, ctx->fb_scaled.p, ob));
     return sync(ctx);
 }
@@ -341,7 +346,8 @@ int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const 
     B2_CUDA(ctx, ctx->fb_scaled.reserve(fb_bytes));
     uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
-    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, b->out_h, b->n_frames, &cs));
+    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, b->out_h, b->n_frames, &cs,
+                        (b->flags & B200TIMG_FAST_SCALE) != 0));
     if (ctx->ev_after_scale) B2_CUDA(ctx, cudaEventRecord(ctx->ev_after_scale, ctx->stream));
     return launch_blocks(ctx, d_fb, nullptr, b->animation ? 2 : 0, b->out_w, b->out_h, b->n_frames, b->flags,
                          b->x_indent_cells, d_out, out_cap, d_offsets);
@@ -363,7 +369,8 @@ static int sixel_batch_phases(b200timg_ctx *ctx, const b200timg_batch *b, const 
     // src/stb-image-source.cc:56-60); then only the pad strip is cleared and composed, exactly the
     // canvas' own start_row = height call (src/sixel-canvas.cc:115-118).
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
-    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, hp, b->n_frames, &cs));
+    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, hp, b->n_frames, &cs,
+                        (b->flags & B200TIMG_FAST_SCALE) != 0));
     if (ctx->ev_after_scale) B2_CUDA(ctx, cudaEventRecord(ctx->ev_after_scale, ctx->stream));
     if (hp != b->out_h) {
         B2_CUDA(ctx, cudaMemset2DAsync(d_fb + (size_t)b->out_h * b->out_w * 4, frame_bytes, 0,

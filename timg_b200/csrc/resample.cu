@@ -496,14 +496,14 @@ struct PlanarGeom { int nix, niy, sp, tp; unsigned grp_magic; const int32_t *til
 constexpr int PTH = 32;          // output rows per tile (= lanes of the horizontal pass)
 constexpr int PNT = 256;
 
-template <int HC, int VC, int PTW, int MINB>
-__global__ void __launch_bounds__(PNT, MINB)
-resample_planar_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, PlanarGeom G) {
+template <int HC, int VC, int PTW>
+__device__ __forceinline__ void resample_planar_body(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, const ResampleParams &P,
+                                                     const PlanarGeom &G, int bx, int by, int f) {
     extern __shared__ float4 s_px[];
     float *S = reinterpret_cast<float *>(s_px);                   // [3][niy][sp]
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.z;
-    const int ox0 = blockIdx.x * PTW, oy0 = blockIdx.y * PTH;
-    const int ix0 = G.tile_ix0[blockIdx.x], iy0 = G.tile_iy0[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ox0 = bx * PTW, oy0 = by * PTH;
+    const int ix0 = G.tile_ix0[bx], iy0 = G.tile_iy0[by];
     const int niy = G.niy, sp = G.sp, tp = G.tp;
     const int splane = niy * sp, tplane = PTH * tp;
     float *T = S + 3 * splane;                                    // [3][PTH][tp]
@@ -708,6 +708,27 @@ resample_planar_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ o
     }
 }
 
+template <int HC, int VC, int PTW, int MINB>
+__global__ void __launch_bounds__(PNT, MINB)
+resample_planar_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, PlanarGeom G) {
+    resample_planar_body<HC, VC, PTW>(in, out, P, G, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// The same tiles driven by a work list (tiles the opaque-only v3 kernel handed back): list[0] = number of
+// 64x32 v3 tiles, list[1 + 3k ..] = (v3 tile x, tile y, frame); each is two 32x32 planar tiles.
+template <int HC, int VC, int MINB>
+__global__ void __launch_bounds__(PNT, MINB)
+resample_planar_list_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, PlanarGeom G,
+                            const uint32_t *__restrict__ list) {
+    const uint32_t n = list[0] * 2u;
+    for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
+        const uint32_t *t = list + 1 + 3 * (e >> 1);
+        const int bx = (int)t[0] * 2 + (int)(e & 1u);
+        if (bx * 32 < P.ow) resample_planar_body<HC, VC, 32>(in, out, P, G, bx, (int)t[1], (int)t[2]);
+        __syncthreads();
+    }
+}
+
 typedef void (*PlanarFn)(const uint32_t *, uint32_t *, ResampleParams, PlanarGeom);
 template <int HC, int PTW, int MINB>
 static PlanarFn planar_v(int vc) {
@@ -788,11 +809,249 @@ resample_copy_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out
     }
 }
 
+
+// ---- v3: opaque tiles, vertical pass first, <= 8 taps per axis ------------------------------
+// What limits the planar kernel above is shared-memory bandwidth and issue slots spent outside the tap
+// sums: it stages three float planes (12 B/px) and every tap of the vertical pass is a 16-byte load.
+// v3 keeps the window as the RAW pixels (4 B/px: a plain 16-byte copy, no decode at staging) and turns
+// bytes into floats at the point of use (PRMT into the mantissa of 2^23, one FSUB), two neighbouring
+// columns per thread; the tap sums work on register PAIRS -- (R,G) of a pixel, (B,B) of two pixels --
+// so one packed instruction does two channels.  Two arithmetic modes:
+//   EXACT  the reference's arithmetic bit for bit (byte * (1/255), every product and sum rounded
+//          separately: scalar FMUL + packed FADD2 -- ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 no
+//          matter what, so the products stay scalar), even/odd horizontal accumulators, analytic alpha
+//          of the all-opaque window, un-weight by 1/alpha, trunc(clamp(v * 255 + 0.5));
+//   FAST   the same filter with FFMA2 and the 1/255 .. *255 round trip dropped: within 1 LSB of the
+//          reference (BASELINE.md's stated gate for the Mitchell path); used where the result feeds the
+//          sixel quantiser, whose own parity is a delta-E tolerance.
+// Tiles whose window is not fully opaque are handed to the planar kernel through a work list.
+struct F2 { float x, y; };
+#ifdef CUSIM
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) { return F2{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+#else
+__device__ __forceinline__ unsigned long long f2_pack(F2 a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ F2 f2_unpack(unsigned long long v) { F2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(r);
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c))); return f2_unpack(r);
+}
+#endif
+// acc = v * c   /   acc += v * c   in the mode's arithmetic
+template <bool EXACT> __device__ __forceinline__ F2 f2_mul(F2 v, float c) {
+    if (EXACT) return F2{fmul(v.x, c), fmul(v.y, c)};
+    return f2_fma(v, F2{c, c}, F2{0.0f, 0.0f});
+}
+template <bool EXACT> __device__ __forceinline__ F2 f2_mac(F2 a, F2 v, float c) {
+    if (EXACT) return f2_add(a, F2{fmul(v.x, c), fmul(v.y, c)});
+    return f2_fma(v, F2{c, c}, a);
+}
+template <bool EXACT> __device__ __forceinline__ float f1_mac(float a, float v, float c) {
+    if (EXACT) return fadd(a, fmul(v, c));
+    return fmaf(v, c, a);
+}
+// byte `sel & 7` of p as a float: exact integer (FAST) or the reference's byte * (1/255) (EXACT)
+template <bool EXACT> __device__ __forceinline__ float byte_val(uint32_t p, uint32_t sel) {
+    const float v = fsub(__uint_as_float(__byte_perm(p, 0x4B000000u, sel)), 8388608.0f);
+    return EXACT ? fmul(v, 1.0f / 255.0f) : v;
+}
+
+struct V3Geom { int nix, niy, sp, tp; unsigned grp_magic; const int32_t *tile_ix0, *tile_iy0; uint32_t *fallback; };   // grp_magic: floor(2^32/(sp/4))+1
+constexpr int V3_TW = 64, V3_TH = 32, V3_NT = 256;
+
+template <int HC, int VC, bool EXACT>
+__global__ void __launch_bounds__(V3_NT, 3)
+resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, V3Geom G) {
+    extern __shared__ float4 s_px[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.z;
+    const int ox0 = blockIdx.x * V3_TW, oy0 = blockIdx.y * V3_TH;
+    const int ix0 = G.tile_ix0[blockIdx.x], iy0 = G.tile_iy0[blockIdx.y];
+    const int niy = G.niy, sp = G.sp, tp = G.tp;
+    uint32_t *S = reinterpret_cast<uint32_t *>(s_px);                        // [niy][sp] raw pixels
+    float2 *TRG = reinterpret_cast<float2 *>(S + niy * sp);                  // [V3_TH][tp]  (R, G) after the vertical pass
+    float *TB = reinterpret_cast<float *>(TRG + V3_TH * tp);                 // [V3_TH][tp]
+    float *s_hc = TB + V3_TH * tp + ((4 - ((V3_TH * tp) & 3)) & 3);         // [V3_TW][8], 16-byte aligned (tp odd, V3_TH * tp * 12 % 16 handled here)
+    float *s_vc = s_hc + V3_TW * 8;                                          // [V3_TH][8]
+    int *s_hfirst = reinterpret_cast<int *>(s_vc + V3_TH * 8);               // [V3_TW]
+    int *s_vfirst = s_hfirst + V3_TW;                                        // [V3_TH]
+    uint32_t *O = S;                                                         // [V3_TH][V3_TW + 1] once S is dead
+    if (tid < V3_TW) {
+        const int ox = ox0 + tid;
+        const bool ok = ox < P.ow;
+        s_hfirst[tid] = ok ? P.h_first[ox] - ix0 : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_hc[tid * 8 + i] = (ok && i < P.h_widest) ? P.h_coeff[(long long)ox * P.h_widest + i] : 0.0f;
+    } else if (tid < V3_TW + V3_TH) {
+        const int t = tid - V3_TW, oy = oy0 + t;
+        const bool ok = oy < P.oh;
+        s_vfirst[t] = ok ? P.v_first[oy] - iy0 : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_vc[t * 8 + i] = (ok && i < P.v_widest) ? P.v_coeff[(long long)oy * P.v_widest + i] : 0.0f;
+    }
+    // ---- stage the window: plain 16-byte copies; cells outside the image are zero (their taps have zero weight)
+    const uint32_t *src = in + (long long)f * P.iw * P.ih;
+    const int ngrp = sp >> 2, n_stage = niy * ngrp;
+    bool ok255 = true;
+    for (int u = tid; u < n_stage; u += V3_NT) {
+        const int ly = (int)__umulhi((unsigned)u, G.grp_magic), g = u - ly * ngrp;
+        const int y = iy0 + ly, x = ix0 + 4 * g;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (y < P.ih && x < P.iw) {
+            raw = __ldg(reinterpret_cast<const uint4 *>(src + (long long)y * P.iw + x));
+            ok255 = ok255 && ((raw.x & raw.y & raw.z & raw.w) >= 0xff000000u);
+        }
+        *reinterpret_cast<uint4 *>(S + ly * sp + 4 * g) = raw;
+    }
+    if (!__syncthreads_and(ok255)) {                              // some pixel of the window has alpha < 255: planar kernel's job
+        if (tid == 0) {
+            const uint32_t k = atomicAdd(G.fallback, 1u);
+            uint32_t *e = G.fallback + 1 + 3 * k;
+            e[0] = blockIdx.x; e[1] = blockIdx.y; e[2] = blockIdx.z;
+        }
+        return;
+    }
+    const uint32_t sel_r = 0x7540u | (P.bgra ? 2u : 0u), sel_g = 0x7541u, sel_b = 0x7540u | (P.bgra ? 0u : 2u);
+    // ---- vertical: T[ty][2cp .. 2cp+1] = sum_k S[vfirst[ty] + k][..] * vc[ty][k], rows in order
+    const int ncp = sp >> 1;
+#pragma unroll 1
+    for (int r = 0; r < V3_TH / 8; ++r) {
+        const int ty = wid + 8 * r;
+        const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + ty * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + ty * 8 + 4);
+        const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const uint32_t *srow = S + s_vfirst[ty] * sp;
+        for (int cp = lane; cp < ncp; cp += 32) {
+            F2 a0, a1, ab;
+#pragma unroll
+            for (int k = 0; k < VC; ++k) {
+                const uint2 pp = *reinterpret_cast<const uint2 *>(srow + k * sp + 2 * cp);
+                const F2 p0 = {byte_val<EXACT>(pp.x, sel_r), byte_val<EXACT>(pp.x, sel_g)};
+                const F2 p1 = {byte_val<EXACT>(pp.y, sel_r), byte_val<EXACT>(pp.y, sel_g)};
+                const F2 pb = {byte_val<EXACT>(pp.x, sel_b), byte_val<EXACT>(pp.y, sel_b)};
+                if (k == 0) { a0 = f2_mul<EXACT>(p0, vc[0]); a1 = f2_mul<EXACT>(p1, vc[0]); ab = f2_mul<EXACT>(pb, vc[0]); }
+                else { a0 = f2_mac<EXACT>(a0, p0, vc[k]); a1 = f2_mac<EXACT>(a1, p1, vc[k]); ab = f2_mac<EXACT>(ab, pb, vc[k]); }
+            }
+            float2 *t = TRG + ty * tp + 2 * cp;
+            t[0] = make_float2(a0.x, a0.y); t[1] = make_float2(a1.x, a1.y);
+            float *tb = TB + ty * tp + 2 * cp;
+            tb[0] = ab.x; tb[1] = ab.y;
+        }
+    }
+    __syncthreads();
+    // ---- horizontal: lane = output row, the warp's column changes with j; taps and start index are warp-uniform
+    const bool hseq = P.h_sequential != 0;
+    const float2 *trow = TRG + lane * tp;
+    const float *brow = TB + lane * tp;
+    float av = 0.0f;                                              // EXACT: vertical tap sum of an all-ones (alpha) column
+    if (EXACT) {
+        const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + lane * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + lane * 8 + 4);
+        const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        av = vc[0];
+#pragma unroll
+        for (int k = 1; k < VC; ++k) av = fadd(av, vc[k]);
+    }
+    uint32_t px[V3_TW / 8];
+#pragma unroll
+    for (int j = 0; j < V3_TW / 8; ++j) {
+        const int tx = wid + 8 * j;
+        const float4 h0 = *reinterpret_cast<const float4 *>(s_hc + tx * 8), h1 = *reinterpret_cast<const float4 *>(s_hc + tx * 8 + 4);
+        const float hc[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float2 *rg = trow + s_hfirst[tx];
+        const float *bb = brow + s_hfirst[tx];
+        F2 c2; float cb, al = 1.0f;
+        if (hseq) {
+            F2 a = f2_mul<EXACT>(F2{rg[0].x, rg[0].y}, hc[0]);
+            float b = EXACT ? fmul(bb[0], hc[0]) : bb[0] * hc[0];
+            float aa = EXACT ? fmul(av, hc[0]) : 0.0f;
+#pragma unroll
+            for (int i = 1; i < (HC < 3 ? HC : 3); ++i) {
+                a = f2_mac<EXACT>(a, F2{rg[i].x, rg[i].y}, hc[i]); b = f1_mac<EXACT>(b, bb[i], hc[i]);
+                if (EXACT) aa = fadd(aa, fmul(av, hc[i]));
+            }
+            c2 = a; cb = b; if (EXACT) al = aa;
+        } else {
+            F2 a0 = f2_mul<EXACT>(F2{rg[0].x, rg[0].y}, hc[0]), a1 = f2_mul<EXACT>(F2{rg[1].x, rg[1].y}, hc[1]);
+            float b0 = EXACT ? fmul(bb[0], hc[0]) : bb[0] * hc[0], b1 = EXACT ? fmul(bb[1], hc[1]) : bb[1] * hc[1];
+            float l0 = EXACT ? fmul(av, hc[0]) : 0.0f, l1 = EXACT ? fmul(av, hc[1]) : 0.0f;
+#pragma unroll
+            for (int i = 2; i < HC; ++i) {
+                if (i & 1) { a1 = f2_mac<EXACT>(a1, F2{rg[i].x, rg[i].y}, hc[i]); b1 = f1_mac<EXACT>(b1, bb[i], hc[i]); if (EXACT) l1 = fadd(l1, fmul(av, hc[i])); }
+                else { a0 = f2_mac<EXACT>(a0, F2{rg[i].x, rg[i].y}, hc[i]); b0 = f1_mac<EXACT>(b0, bb[i], hc[i]); if (EXACT) l0 = fadd(l0, fmul(av, hc[i])); }
+            }
+            c2 = EXACT ? f2_add(a0, a1) : F2{a0.x + a1.x, a0.y + a1.y};
+            cb = EXACT ? fadd(b0, b1) : b0 + b1;
+            if (EXACT) al = fadd(l0, l1);
+        }
+        if (EXACT) {
+            float v[7];
+            v[0] = c2.x; v[1] = c2.y; v[2] = cb; v[3] = al; v[4] = c2.x; v[5] = c2.y; v[6] = cb;
+            px[j] = compose_at(P.cs, encode_px(v), ox0 + tx, oy0 + lane);
+        } else {
+            const uint32_t r8 = __float2uint_rz(fminf(fmaxf(c2.x + 0.5f, 0.0f), 255.0f));
+            const uint32_t g8 = __float2uint_rz(fminf(fmaxf(c2.y + 0.5f, 0.0f), 255.0f));
+            const uint32_t b8 = __float2uint_rz(fminf(fmaxf(cb + 0.5f, 0.0f), 255.0f));
+            px[j] = pack_rgba(r8, g8, b8, 0xffu);                     // opaque in, opaque out: nothing to compose
+        }
+    }
+    __syncthreads();                                              // every warp is done reading T (O aliases S, which died earlier, but keep the order simple)
+#pragma unroll
+    for (int j = 0; j < V3_TW / 8; ++j) O[lane * (V3_TW + 1) + wid + 8 * j] = px[j];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V3_TH / 8; ++i) {
+        const int ty = wid + 8 * i, oy = oy0 + ty;
+        if (oy < P.oh) {
+            uint32_t *orow = out + ((long long)f * P.out_frame_rows + oy) * P.ow + ox0;
+            if (ox0 + lane < P.ow) orow[lane] = O[ty * (V3_TW + 1) + lane];
+            if (ox0 + lane + 32 < P.ow) orow[lane + 32] = O[ty * (V3_TW + 1) + lane + 32];
+        }
+    }
+}
+
+typedef void (*V3Fn)(const uint32_t *, uint32_t *, ResampleParams, V3Geom);
+template <int HC, bool EXACT>
+static V3Fn v3_v(int vc) {
+    switch (vc) {
+    case 2: return resample_v3_kernel<HC, 2, EXACT>;
+    case 4: return resample_v3_kernel<HC, 4, EXACT>;
+    case 6: return resample_v3_kernel<HC, 6, EXACT>;
+    default: return resample_v3_kernel<HC, 8, EXACT>;
+    }
+}
+template <bool EXACT>
+static V3Fn v3_h(int hc, int vc) {
+    switch (hc) {
+    case 2: return v3_v<2, EXACT>(vc);
+    case 4: return v3_v<4, EXACT>(vc);
+    case 6: return v3_v<6, EXACT>(vc);
+    default: return v3_v<8, EXACT>(vc);
+    }
+}
+typedef void (*PlanarListFn)(const uint32_t *, uint32_t *, ResampleParams, PlanarGeom, const uint32_t *);
+template <int HC>
+static PlanarListFn planar_list_v(int vc) {
+    switch (vc) {
+    case 2: return resample_planar_list_kernel<HC, 2, 3>;
+    case 4: return resample_planar_list_kernel<HC, 4, 3>;
+    case 6: return resample_planar_list_kernel<HC, 6, 3>;
+    default: return resample_planar_list_kernel<HC, 8, 3>;
+    }
+}
+static PlanarListFn planar_list_h(int hc, int vc) {
+    switch (hc) {
+    case 2: return planar_list_v<2>(vc);
+    case 4: return planar_list_v<4>(vc);
+    case 6: return planar_list_v<6>(vc);
+    default: return planar_list_v<8>(vc);
+    }
+}
+
 // ---- plan cache + upload ----------------------------------------------------------------
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out,
-                 int ow, int oh, int out_frame_rows, int n_frames, const ComposeSpec *cs) {
+                 int ow, int oh, int out_frame_rows, int n_frames, const ComposeSpec *cs, int fast) {
     if (out_frame_rows < oh) return ctx->fail(B200TIMG_EINVAL, "scale: frame rows < out height");
     if ((reinterpret_cast<uintptr_t>(d_in) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 3))
         return ctx->fail(B200TIMG_EINVAL, "scale: pixel buffers must be 4-byte aligned");
@@ -848,35 +1107,63 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
         resample_copy_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, P);
     } else {
         if (n_frames > 65535) return ctx->fail(B200TIMG_EINVAL, "scale: too many frames for one launch");
-        // fast path: both axes need <= 8 taps -> fixed-tap kernel on 64x16 tiles
-        // fastest path: vertical pass first, <= 8 taps per axis, 16-byte aligned rows -> planar kernel
+        // fastest path: vertical pass first, <= 8 taps per axis, 16-byte aligned rows -> v3 kernel (opaque tiles)
+        // with the planar kernel taking the tiles that contain transparency
         if (pl->vertical_first && pl->h.widest <= 8 && pl->v.widest <= 8 && (iw & 3) == 0 &&
             (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !getenv("B200TIMG_NO_PLANAR") && !getenv("B200TIMG_NO_FIXED")) {
             const int hc = fixed_class(pl->h.widest), vc = fixed_class(pl->v.widest);
+            auto tile_origins = [&](const AxisTable &T, int n_out, int tile, int taps, bool align4, std::vector<int32_t> &orig) -> int {
+                const int nt = (n_out + tile - 1) / tile;
+                orig.resize(nt);
+                int span = 1;
+                for (int j = 0; j < nt; ++j) {
+                    int lo = 0x7fffffff, hi = -1;
+                    for (int x = j * tile; x < std::min(n_out, (j + 1) * tile); ++x) { lo = std::min(lo, T.first[x]); hi = std::max(hi, T.first[x] + taps - 1); }
+                    if (align4) lo &= ~3;                            // aligned 16-byte loads
+                    orig[j] = lo; span = std::max(span, hi - lo + 1);
+                }
+                return span;
+            };
+            std::vector<int32_t> tix, tiy, tix3;
             const int ptw = 32;
-            const int ntx = (ow + ptw - 1) / ptw, nty = (oh + PTH - 1) / PTH;
-            std::vector<int32_t> tix(ntx), tiy(nty);
-            int nix = 1, niy = 1;
-            for (int j = 0; j < ntx; ++j) {
-                int lo = 0x7fffffff, hi = -1;
-                for (int x = j * ptw; x < std::min(ow, (j + 1) * ptw); ++x) { lo = std::min(lo, pl->h.first[x]); hi = std::max(hi, pl->h.first[x] + hc - 1); }
-                lo &= ~3;                                    // aligned 16-byte loads
-                tix[j] = lo; nix = std::max(nix, hi - lo + 1);
-            }
-            for (int j = 0; j < nty; ++j) {
-                int lo = 0x7fffffff, hi = -1;
-                for (int y = j * PTH; y < std::min(oh, (j + 1) * PTH); ++y) { lo = std::min(lo, pl->v.first[y]); hi = std::max(hi, pl->v.first[y] + vc - 1); }
-                tiy[j] = lo; niy = std::max(niy, hi - lo + 1);
-            }
+            const int nix = tile_origins(pl->h, ow, ptw, hc, true, tix), niy = tile_origins(pl->v, oh, PTH, vc, false, tiy);
+            const int ntx = (int)tix.size(), nty = (int)tiy.size();
             const int sp = (nix + 3) & ~3, tp = sp | 1;   // odd T pitch >= the 4-column groups written per row
             const size_t psmem = sizeof(float) * (3 * ((size_t)niy * sp + (size_t)PTH * tp) + 4 + (size_t)ptw * 8 + PTH * 8) + sizeof(int) * (ptw + PTH);
             const size_t smem_cap = 75 * 1024;           // 3 CTAs/SM (80 registers): 7.96 ms vs 10.2 ms at 2 CTAs/SM, 148 C2 frames
-            if (psmem <= smem_cap && (size_t)PTH * (ptw + 1) <= 3 * (size_t)niy * sp) {
-                B2_CUDA(ctx, ctx->misc.reserve(4096 + sizeof(int32_t) * (size_t)(ntx + nty)));
+            const bool planar_ok = psmem <= smem_cap && (size_t)PTH * (ptw + 1) <= 3 * (size_t)niy * sp;
+            // v3 geometry: 64 x 32 output tiles
+            const int nix3 = tile_origins(pl->h, ow, V3_TW, hc, true, tix3);
+            const int ntx3 = (int)tix3.size();
+            const int sp3 = (nix3 + 3) & ~3, tp3 = sp3 | 1;
+            const size_t v3smem = sizeof(uint32_t) * (size_t)niy * sp3 + (sizeof(float2) + sizeof(float)) * (size_t)V3_TH * tp3 + 16 +
+                                  sizeof(float) * ((size_t)V3_TW * 8 + V3_TH * 8) + sizeof(int) * (V3_TW + V3_TH);
+            const bool v3_ok = planar_ok && !getenv("B200TIMG_NO_V3") && v3smem <= 100 * 1024 && (size_t)V3_TH * (V3_TW + 1) <= (size_t)niy * sp3;
+            if (planar_ok) {
+                B2_CUDA(ctx, ctx->misc.reserve(4096 + sizeof(int32_t) * (size_t)(ntx + nty + ntx3)));
                 int32_t *d_t = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 4096);
                 B2_CUDA(ctx, cudaMemcpyAsync(d_t, tix.data(), sizeof(int32_t) * ntx, cudaMemcpyHostToDevice, ctx->stream));
                 B2_CUDA(ctx, cudaMemcpyAsync(d_t + ntx, tiy.data(), sizeof(int32_t) * nty, cudaMemcpyHostToDevice, ctx->stream));
+                B2_CUDA(ctx, cudaMemcpyAsync(d_t + ntx + nty, tix3.data(), sizeof(int32_t) * ntx3, cudaMemcpyHostToDevice, ctx->stream));
                 PlanarGeom PG{nix, niy, sp, tp, (unsigned)(0x100000000ull / (unsigned)(sp / 4)) + 1u, d_t, d_t + ntx};
+                if (v3_ok) {
+                    const size_t list_bytes = sizeof(uint32_t) * (1 + 3 * (size_t)ntx3 * nty * n_frames);
+                    B2_CUDA(ctx, ctx->scale_list.reserve(list_bytes));
+                    uint32_t *d_list = ctx->scale_list.as<uint32_t>();
+                    B2_CUDA(ctx, cudaMemsetAsync(d_list, 0, sizeof(uint32_t), ctx->stream));
+                    V3Geom VG{nix3, niy, sp3, tp3, (unsigned)(0x100000000ull / (unsigned)(sp3 / 4)) + 1u, d_t + ntx + nty, d_t + ntx, d_list};
+                    V3Fn fn = fast ? v3_h<false>(hc, vc) : v3_h<true>(hc, vc);
+                    B2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    B2_KERNEL(ctx, fast ? "resample_v3_fast_kernel" : "resample_v3_exact_kernel");
+                    fn<<<dim3(ntx3, nty, n_frames), V3_NT, v3smem, ctx->stream>>>(in, out, P, VG);
+                    B2_LAUNCH_CHECK(ctx);
+                    PlanarListFn lf = planar_list_h(hc, vc);              // tiles with transparency (none for photos / video)
+                    B2_CUDA(ctx, cudaFuncSetAttribute(lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+                    B2_KERNEL(ctx, "resample_planar_list_kernel");
+                    lf<<<ctx->sm_count * 3, PNT, psmem, ctx->stream>>>(in, out, P, PG, d_list);
+                    B2_LAUNCH_CHECK(ctx);
+                    return B200TIMG_OK;
+                }
                 PlanarFn fn = planar_h<32, 3>(hc, vc);
                 B2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
                 const dim3 grid(ntx, nty, n_frames);
