@@ -286,3 +286,41 @@ def ref_compose_bg(fb, bg, pattern=0, pw=0, ph=0, start_row=0, has_bg=True):
     h, w = out.shape[:2]
     ref().ref_compose(_ptr(out), w, h, int(has_bg), bg, pattern, pw, ph, start_row)
     return out
+
+
+# ---- native multi-threaded CPU baseline (oracle/cpu_pipeline.c): no Python inside the timed region
+def _stage_ptrs():
+    """(scale, compose, kind): the reference's own TUs when oracle/_ref is built, else the restatements."""
+    cast = lambda f: C.cast(f, C.c_void_p)
+    if have_ref():
+        R = ref()
+        return cast(R.ref_scale), cast(R.ref_compose), "reference STB TU + reference AlphaComposeBackground (oracle/_ref)"
+    L = lib()
+    return cast(L.orc_stb_resize7), cast(L.orc_compose_bg), "STB + compose restatements (oracle/*.c)"
+
+
+def cpu_sixel_jobs(frames, n_jobs, ow, oh, bg, threads, mode=0, has_bg=True):
+    """Scale -> compose -> pad -> libsixel restatement for n_jobs frames (job j = frames[j % len]) on
+    `threads` native threads.  Returns (wall seconds, encoded sizes, description of the stages)."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    n, ih, iw = frames.shape[:3]
+    L = lib()
+    f = _sig(L, "orc_cpu_sixel_jobs", C.c_double, [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
+    sf, cf, what = _stage_ptrs()
+    sizes = np.zeros(n_jobs, np.int64)
+    dt = f(_ptr(frames), n, iw, ih, n_jobs, ow, oh, int(has_bg), bg, mode, threads, sf, cf, sizes.ctypes.data)
+    return dt, sizes, what + "; sixel = libsixel restatement (libsixel is not vendored in the reference)"
+
+
+def cpu_blocks_jobs(frames, n_jobs, ow, oh, bg, threads, flags=0, animation=False, has_bg=True):
+    """Scale -> compose -> UnicodeBlockCanvas::Send through the reference's own TUs (needs oracle/_ref)."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    n, ih, iw = frames.shape[:3]
+    L, R = lib(), ref()
+    f = _sig(L, "orc_cpu_blocks_jobs", C.c_double, [u8p] + [C.c_int] * 7 + [C.c_uint32, C.c_int, C.c_int, C.c_int] +
+             [C.c_void_p] * 5)
+    cast = lambda fn: C.cast(fn, C.c_void_p)
+    dt = f(_ptr(frames), n, iw, ih, n_jobs, ow, oh, int(has_bg), bg, flags, int(animation), threads,
+           cast(R.ref_scale), cast(R.ref_compose), cast(R.ref_blocks_new), cast(R.ref_blocks_send), cast(R.ref_blocks_free))
+    return dt, "reference TUs (oracle/_ref): ImageScaler(STB) + AlphaComposeBackground + UnicodeBlockCanvas::Send to /dev/null"

@@ -234,7 +234,11 @@ int launch_sixel_dither(b200timg_ctx *ctx, const uint32_t *fb, int w, int h, int
     }
     G.bands_per_cta = (G.nb32 + per_frame - 1) / per_frame;
     per_frame = (G.nb32 + G.bands_per_cta - 1) / G.bands_per_cta;
-    const int rounds = (G.bands_per_cta + D2_WMAX - 1) / D2_WMAX;
+    // warps per CTA: full rounds over the CTA's bands.  Fewer warps = more rounds but a smaller share of the time spent
+    // filling and draining the band pipeline (each band starts ~80 columns behind the one above).
+    int wmax = D2_WMAX;
+    if (const char *e = getenv("B200TIMG_DITHER_WARPS")) wmax = std::max(1, std::min(atoi(e), D2_WMAX));
+    const int rounds = (G.bands_per_cta + wmax - 1) / wmax;
     G.nwarps = (G.bands_per_cta + rounds - 1) / rounds;
     if (G.bands_per_cta > 2048) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too tall");
     const size_t smem = 32768 + (size_t)G.nwarps * D2_WARP_SMEM;
