@@ -231,6 +231,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernels-only", action="store_true", help="print just the per-kernel table (tuning runs)")
+    ap.add_argument("--yuv", action="store_true",
+                    help="feed decoder-style I420 frames (1.5 B/px) through the fused colour-conversion + bilinear scaler "
+                         "(the video source's sws_scale, src/video-source.cc:352-354) instead of RGBA through ImageScaler")
     ap.add_argument("--exact-scale", action="store_true",
                     help="bit-exact scaler arithmetic on the sixel path instead of the <= 1 LSB fused-multiply-add mode")
     args = ap.parse_args()
@@ -267,10 +270,26 @@ def main():
     assert stream.cuda_stream != 0
     L = timg_b200.lib()
     frames = frames_torch(synth, cfg, F, SEED + rank * F, dev)
+    src_fmt, frame_bytes = 0, iw * ih * 4
+    if args.yuv:                                   # BT.601 limited-range I420 of the same frames (2x2 box chroma)
+        def to_i420(fr):
+            c = fr[..., :3].to(torch.float32)
+            r, g, bl = c[..., 0], c[..., 1], c[..., 2]
+            y = 16 + 0.256788 * r + 0.504129 * g + 0.097906 * bl
+            u = 128 - 0.148223 * r - 0.290993 * g + 0.439216 * bl
+            v = 128 + 0.439216 * r - 0.367788 * g - 0.071427 * bl
+            box = lambda p: p.reshape(ih // 2, 2, iw // 2, 2).mean((1, 3))
+            q = lambda p: p.round().clamp(0, 255).to(torch.uint8).reshape(-1)
+            return torch.cat([q(y), q(box(u)), q(box(v))])
+        yuv = torch.empty((F, iw * ih * 3 // 2), dtype=torch.uint8, device=dev)
+        for i in range(F):
+            yuv[i] = to_i420(frames[i])
+        frames, src_fmt, frame_bytes = yuv, timg_b200.FMT_I420, iw * ih * 3 // 2
+        config["source"] = "I420 (BT.601 limited range), colour conversion fused into the bilinear scaler"
     torch.cuda.synchronize(dev)
     # the sixel path's scaler runs in the <= 1 LSB mode unless --exact-scale; block modes are always bit-exact
     flags = cfg["flags"] | (FAST_SCALE if sixel and not args.exact_scale else 0)
-    b = timg_b200.Batch(n_frames=F, src_w=iw, src_h=ih, src_fmt=0, out_w=ow, out_h=oh, has_bg=1,
+    b = timg_b200.Batch(n_frames=F, src_w=iw, src_h=ih, src_fmt=src_fmt, out_w=ow, out_h=oh, has_bg=1,
                         bg=timg_b200.rgba_u32(*BG), pattern=0, pattern_w=0, pattern_h=0, flags=flags, x_indent_cells=0,
                         animation=cfg["animation"])
     dev_call = L.b200timg_sixel_batch_dev if sixel else L.b200timg_blocks_batch_dev
@@ -354,7 +373,7 @@ def main():
         dom = max(rep, key=lambda k: rep[k][1])
         n, ms = rep[dom]
         # read every source pixel once + write every encoded byte once (+ previous scaled frame for deltas)
-        alg_bytes = F * (4 * iw * ih) + total_bytes + (4 * ow * oh * (F - 1) if cfg["animation"] else 0)
+        alg_bytes = F * frame_bytes + total_bytes + (4 * ow * oh * (F - 1) if cfg["animation"] else 0)
         peak, how = peak_hbm()
         achieved = alg_bytes / (ms / n / 1e3) / 1e9
         traffic = None       # dram__bytes_read+write of that kernel per launch, from the committed ncu capture
@@ -392,10 +411,10 @@ def main():
     if not args.no_e2e:
         Fe = F
         try:
-            h_in = torch.empty((Fe, ih, iw, 4), dtype=torch.uint8, pin_memory=True)
+            h_in = torch.empty((Fe,) + tuple(frames.shape[1:]), dtype=torch.uint8, pin_memory=True)
         except RuntimeError:
             Fe = max(1, F // 8)
-            h_in = torch.empty((Fe, ih, iw, 4), dtype=torch.uint8, pin_memory=True)
+            h_in = torch.empty((Fe,) + tuple(frames.shape[1:]), dtype=torch.uint8, pin_memory=True)
         h_in.copy_(frames[:Fe])
         h_out = torch.empty(int(total_bytes * Fe / F * 1.1) + 4096, dtype=torch.uint8, pin_memory=True)
         h_offs = np.zeros(Fe + 1, np.uint64)
@@ -410,11 +429,11 @@ def main():
         e2e_step()
         # raw pinned H2D rate of this box, for context: the e2e number cannot exceed it
         torch.cuda.synchronize(dev)
-        nprobe = max(1, min(Fe, (1 << 30) // (iw * ih * 4)))
+        nprobe = max(1, min(Fe, (1 << 30) // frame_bytes))
         t0 = time.perf_counter()
         frames[:nprobe].copy_(h_in[:nprobe], non_blocking=True)
         torch.cuda.synchronize(dev)
-        h2d_gbs = nprobe * iw * ih * 4 / (time.perf_counter() - t0) / 1e9
+        h2d_gbs = nprobe * frame_bytes / (time.perf_counter() - t0) / 1e9
         if world > 1:
             dist.barrier()
         ke = max(1, min(args.steps, 5))
@@ -428,10 +447,10 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": world * Fe * ke * iw * ih / 1e6 / dt, "unit": "Mpx/s",
-               "h2d_bytes_per_step": int(Fe * iw * ih * 4), "d2h_bytes_per_step": int(h_offs[Fe]) + 8 * (Fe + 1),
+               "h2d_bytes_per_step": int(Fe * frame_bytes), "d2h_bytes_per_step": int(h_offs[Fe]) + 8 * (Fe + 1),
                "frames_per_step": Fe, "steps": ke,
                "api": ("b200timg_sixel_batch" if sixel else "b200timg_blocks_batch") + " (host buffers, pinned)",
-               "pcie_h2d_gbs_measured": h2d_gbs, "pcie_bound_mpx_s": h2d_gbs * 1e9 / 4 / 1e6, "numa": numa}
+               "pcie_h2d_gbs_measured": h2d_gbs, "pcie_bound_mpx_s": h2d_gbs * 1e9 / (frame_bytes / (iw * ih)) / 1e6, "numa": numa}
         del h_in, h_out
 
     # ---- the reference's CPU path beside it (rank 0, N=1 only): a bounded sample on native threads

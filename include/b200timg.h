@@ -52,10 +52,21 @@ extern "C" {
  * ImageScaler::Scale's instead of bit-identical.  Meant for -p sixel, whose quantiser is compared
  * by a colour-difference tolerance anyway; never set it for the block modes' byte parity. */
 #define B200TIMG_FAST_SCALE 8
+/* batch flag: scale RGBA with the libswscale-style bilinear (triangle) filter of the reference's default
+ * build (src/image-scaler.cc:45-72) instead of the STB build's Mitchell/box.  libswscale is not part of
+ * the reference tree and its result is version/SIMD dependent: parity unpinned, distance measured in tests. */
+#define B200TIMG_BILINEAR_SCALE 16
 
 /* input colour formats: ImageScaler::ColorFmt, src/image-scaler.h:26-29 */
 #define B200TIMG_FMT_RGBA  0
 #define B200TIMG_FMT_RGB32 1    /* BGRA in memory */
+/* decoder output of the video source (src/video-source.cc:59-89): planar / semi-planar YUV 4:2:0, converted
+ * and scaled to RGBA in one pass (batch entry points and b200timg_yuv_scale only).  A frame is w*h luma bytes
+ * followed by the chroma planes (I420: U then V, each (w/2)*(h/2); NV12: interleaved UV); w and h even.
+ * Limited ("TV") range BT.601 unless B200TIMG_FMT_FULL_RANGE is or'ed in (the reference's YUVJ formats). */
+#define B200TIMG_FMT_I420  2
+#define B200TIMG_FMT_NV12  3
+#define B200TIMG_FMT_FULL_RANGE 0x10
 
 typedef struct b200timg_ctx b200timg_ctx;
 
@@ -92,9 +103,15 @@ int b200timg_as256(uint32_t rgba);
  * alpha-weighted, per axis.  in: iw*ih*4 bytes, out: ow*oh*4 bytes. */
 int b200timg_scale_rgba(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt,
                         uint8_t *out, int ow, int oh);
-/* Same with fast != 0 selecting the <= 1 LSB arithmetic described at B200TIMG_FAST_SCALE. */
+/* mode 0: as above; 1: the <= 1 LSB arithmetic described at B200TIMG_FAST_SCALE; 2: the libswscale-style
+ * bilinear filter described at B200TIMG_BILINEAR_SCALE. */
 int b200timg_scale_rgba_mode(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt,
                              uint8_t *out, int ow, int oh, int fast);
+
+/* The video source's sws_scale(decoder YUV -> RGBA at the target size), src/video-source.cc:59-89,352-354:
+ * fmt = B200TIMG_FMT_I420 or _NV12 (| B200TIMG_FMT_FULL_RANGE); in: iw*ih*3/2 bytes; out: ow*oh*4 bytes. */
+int b200timg_yuv_scale(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt,
+                       uint8_t *out, int ow, int oh);
 
 /* Framebuffer::AlphaComposeBackground (src/framebuffer.cc:108-150), in place on fb.
  * has_bg==0 models a null bgcolor_getter ("-b none"); the lazy getter itself stays on

@@ -324,3 +324,125 @@ def cpu_blocks_jobs(frames, n_jobs, ow, oh, bg, threads, flags=0, animation=Fals
     dt = f(_ptr(frames), n, iw, ih, n_jobs, ow, oh, int(has_bg), bg, flags, int(animation), threads,
            cast(R.ref_scale), cast(R.ref_compose), cast(R.ref_blocks_new), cast(R.ref_blocks_send), cast(R.ref_blocks_free))
     return dt, "reference TUs (oracle/_ref): ImageScaler(STB) + AlphaComposeBackground + UnicodeBlockCanvas::Send to /dev/null"
+
+
+# ---- libswscale-style bilinear scaling and YUV 4:2:0 -> RGBA (PARITY UNPINNED: libswscale is not in the reference tree)
+def _tri_axis(src, dst):
+    """Float64 statement of the triangle filter the device tables use: centre-aligned sampling, half-width
+    max(1, src/dst), edge clamp by folding weights onto the border sample.  Returns a dense [dst, src] matrix."""
+    r = src / dst
+    half = max(r, 1.0)
+    M = np.zeros((dst, src))
+    for i in range(dst):
+        c = (i + 0.5) * r - 0.5
+        lo, hi = int(np.ceil(c - half)), int(np.floor(c + half))
+        if lo == hi and half == 1.0:
+            hi = lo + 1
+        w = np.maximum(0.0, 1.0 - np.abs(np.arange(lo, hi + 1) - c) / half)
+        w = w / w.sum()
+        for j, v in zip(range(lo, hi + 1), w):
+            M[i, min(max(j, 0), src - 1)] += v
+    return M
+
+
+def bilinear_rgba_np(img, ow, oh, fmt=0):
+    img = np.asarray(img, dtype=np.float64)
+    ih, iw = img.shape[:2]
+    out = np.einsum("oy,yxc->oxc", _tri_axis(ih, oh), np.einsum("px,yxc->ypc", _tri_axis(iw, ow), img))
+    if fmt == 1:
+        out = out[..., [2, 1, 0, 3]]
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def yuv420_to_rgba_np(yuv, iw, ih, ow, oh, nv12=False, full_range=False):
+    """Float64 statement of timg_b200/csrc/bilinear.cu's yuv420_rgba_kernel (BT.601)."""
+    yuv = np.asarray(yuv, dtype=np.uint8).reshape(-1)
+    cw, ch = iw // 2, ih // 2
+    Y = yuv[: iw * ih].reshape(ih, iw).astype(np.float64)
+    if nv12:
+        uv = yuv[iw * ih:].reshape(ch, cw, 2).astype(np.float64)
+        U, V = uv[..., 0], uv[..., 1]
+    else:
+        U = yuv[iw * ih: iw * ih + cw * ch].reshape(ch, cw).astype(np.float64)
+        V = yuv[iw * ih + cw * ch:].reshape(ch, cw).astype(np.float64)
+    # chroma is carried at half the output width (libswscale's packed-RGB writers without SWS_FULL_CHR_H_INT):
+    # the two pixels of an output pair share one chroma sample
+    cow = (ow + 1) // 2
+    y = _tri_axis(ih, oh) @ Y @ _tri_axis(iw, ow).T
+    Mv = _tri_axis(ch, oh)
+    if (ow, oh) == (iw, ih):        # unscaled: chroma rows are replicated (2x2 blocks share a sample), as libswscale's unscaled path does
+        Mv = np.zeros((oh, ch))
+        Mv[np.arange(oh), np.arange(oh) // 2] = 1.0
+    chroma = lambda P: np.repeat(Mv @ P @ _tri_axis(cw, cow).T, 2, 1)[:, :ow] - 128.0
+    u, v = chroma(U), chroma(V)
+    if full_range:
+        r, g, b = y + 1.402 * v, y - 0.344136 * u - 0.714136 * v, y + 1.772 * u
+    else:
+        yl = 1.164383 * (y - 16.0)
+        r, g, b = yl + 1.596027 * v, yl - 0.391762 * u - 0.812968 * v, yl + 2.017232 * u
+    out = np.stack([r, g, b, np.full_like(r, 255.0)], -1)
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def rgba_to_i420_np(img):
+    """BT.601 limited-range RGB -> I420 bytes (2x2 box chroma), for building YUV test inputs from RGBA frames."""
+    img = np.asarray(img, dtype=np.float64)
+    r, g, b = img[..., 0], img[..., 1], img[..., 2]
+    y = 16 + 0.256788 * r + 0.504129 * g + 0.097906 * b
+    u = 128 - 0.148223 * r - 0.290993 * g + 0.439216 * b
+    v = 128 + 0.439216 * r - 0.367788 * g - 0.071427 * b
+    h, w = y.shape
+    box = lambda p: p.reshape(h // 2, 2, w // 2, 2).mean((1, 3))
+    q = lambda p: np.clip(np.rint(p), 0, 255).astype(np.uint8)
+    return np.concatenate([q(y).reshape(-1), q(box(u)).reshape(-1), q(box(v)).reshape(-1)])
+
+
+_SWS = None
+
+
+def swscale():
+    """The libswscale that happens to be bundled with the image's OpenCV wheel (9.1.100), or None.  NOT the
+    reference's pinned dependency (none is pinned, CMakeLists.txt:72-74): informational distance checks only."""
+    global _SWS
+    if _SWS is None:
+        import glob
+        import sysconfig
+        _SWS = False
+        for d in glob.glob(os.path.join(sysconfig.get_paths()["purelib"], "opencv_python*.libs")):
+            pending = sorted(glob.glob(os.path.join(d, "*.so*")))
+            for _ in range(6):                       # the wheel's private libraries depend on each other
+                nxt = []
+                for p in pending:
+                    try:
+                        C.CDLL(p, mode=C.RTLD_GLOBAL)
+                    except OSError:
+                        nxt.append(p)
+                pending = nxt
+            cand = glob.glob(os.path.join(d, "libswscale-*.so*"))
+            if cand and not pending:
+                L = C.CDLL(cand[0])
+                L.sws_getContext.restype = C.c_void_p
+                L.sws_getContext.argtypes = [C.c_int] * 7 + [C.c_void_p] * 3
+                L.sws_scale.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+                L.sws_freeContext.argtypes = [C.c_void_p]
+                _SWS = L
+                break
+    return _SWS or None
+
+
+def sws_scale_np(planes, strides, iw, ih, src_fmt, ow, oh):
+    """sws_getContext(src_fmt -> AV_PIX_FMT_RGBA, SWS_BILINEAR) + sws_scale, as the reference calls it
+    (src/image-scaler.cc:50-66, src/video-source.cc:74-77,352-354).  src_fmt: 0 = YUV420P, 23 = NV12, 26 = RGBA."""
+    L = swscale()
+    ctx = L.sws_getContext(iw, ih, src_fmt, ow, oh, 26, 2, None, None, None)
+    assert ctx
+    out = np.zeros((oh + 1, ow, 4), np.uint8)          # Framebuffer allocates one spare row for sws overruns (src/framebuffer.cc:62)
+    planes = [np.ascontiguousarray(p) for p in planes]
+    src = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [None] * (4 - len(planes))))
+    sst = (C.c_int * 4)(*(list(strides) + [0] * (4 - len(strides))))
+    dst = (C.c_void_p * 4)(out.ctypes.data, None, None, None)
+    dstr = (C.c_int * 4)(ow * 4, 0, 0, 0)
+    L.sws_scale(ctx, src, sst, 0, ih, dst, dstr)
+    L.sws_freeContext(ctx)
+    return out[:oh].copy()

@@ -16,8 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200timg.so")
 
 OK, EINVAL, ENOMEM, ECUDA, ENOSPC, ENODEV = 0, -1, -2, -3, -4, -5
-QUARTER, UPPER, COLOR8, FAST_SCALE = 1, 2, 4, 8
-FMT_RGBA, FMT_RGB32 = 0, 1
+QUARTER, UPPER, COLOR8, FAST_SCALE, BILINEAR_SCALE = 1, 2, 4, 8, 16
+FMT_RGBA, FMT_RGB32, FMT_I420, FMT_NV12, FMT_FULL_RANGE = 0, 1, 2, 3, 0x10
 
 u8p = C.POINTER(C.c_uint8)
 u64p = C.POINTER(C.c_uint64)
@@ -48,6 +48,7 @@ ABI = {
     "b200timg_as256": (C.c_int, [C.c_uint32]),
     "b200timg_scale_rgba": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]),
     "b200timg_scale_rgba_mode": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int]),
+    "b200timg_yuv_scale": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]),
     "b200timg_compose_bg": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
                                       C.c_int, C.c_int, C.c_int]),
     "b200timg_has_transparency": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
@@ -174,10 +175,19 @@ class Context:
 
     # ---- single-frame host entry points (numpy in / numpy or bytes out)
     def scale(self, img, ow, oh, fmt=FMT_RGBA, fast=False):
+        """fast: False/0 bit-exact STB semantics, True/1 <= 1 LSB mode, 2 libswscale-style bilinear."""
         img = np.ascontiguousarray(img, dtype=np.uint8)
         ih, iw = img.shape[:2]
         out = np.empty((oh, ow, 4), np.uint8)
         self._chk(lib().b200timg_scale_rgba_mode(self.h, _np_ptr(img), iw, ih, fmt, _np_ptr(out), ow, oh, int(fast)))
+        return out
+
+    def yuv_scale(self, yuv, iw, ih, ow, oh, fmt=FMT_I420):
+        """yuv: flat uint8 array of iw*ih*3/2 bytes (I420 or NV12) -> RGBA [oh, ow, 4]."""
+        yuv = np.ascontiguousarray(yuv, dtype=np.uint8).reshape(-1)
+        assert yuv.size == iw * ih * 3 // 2
+        out = np.empty((oh, ow, 4), np.uint8)
+        self._chk(lib().b200timg_yuv_scale(self.h, _np_ptr(yuv), iw, ih, fmt, _np_ptr(out), ow, oh))
         return out
 
     def compose_bg(self, fb, bg, pattern=0, pw=0, ph=0, start_row=0, has_bg=True):

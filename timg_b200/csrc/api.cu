@@ -69,7 +69,7 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->in_stage.release(); ctx->fb_scaled.release(); ctx->prev_stage.release();
     ctx->out_stage.release(); ctx->offsets.release(); ctx->cells.release(); ctx->rows.release();
-    ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release(); ctx->scale_list.release();
+    ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release(); ctx->scale_list.release(); ctx->tri_tables.release();
     ctx->pinned.release(); ctx->pinned_io.release();
     for (int i = 0; i < 2; ++i) { ctx->pipe_in[i].release(); ctx->pipe_out[i].release(); }
     if (ctx->pipe_ready) {
@@ -286,7 +286,22 @@ int b200timg_scale_rgba_mode(b200timg_ctx *ctx, const uint8_t *in, int iw, int i
     B2_CUDA(ctx, ctx->in_stage.reserve(ib));
     B2_CUDA(ctx, ctx->fb_scaled.reserve(ob));
     B2_TRY(upload(ctx, ctx->in_stage.p, in, ib));
-    B2_TRY(launch_scale(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1, nullptr, fast));
+    if (fast == 2) B2_TRY(launch_scale_bilinear(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1, nullptr));
+    else B2_TRY(launch_scale(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1, nullptr, fast));
+    B2_TRY(download(ctx, out, ctx->fb_scaled.p, ob));
+    return sync(ctx);
+}
+
+int b200timg_yuv_scale(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int fmt, uint8_t *out, int ow, int oh) {
+    B2_TRY(check_ctx(ctx));
+    const int f = fmt & 0xf;
+    if (!in || !out || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0 || (f != B200TIMG_FMT_I420 && f != B200TIMG_FMT_NV12))
+        return ctx->fail(B200TIMG_EINVAL, "yuv_scale: bad args");
+    const size_t ib = (size_t)iw * ih + 2 * (size_t)(iw / 2) * (ih / 2), ob = (size_t)ow * oh * 4;
+    B2_CUDA(ctx, ctx->in_stage.reserve(ib));
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(ob));
+    B2_TRY(upload(ctx, ctx->in_stage.p, in, ib));
+    B2_TRY(launch_yuv_scale(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1));
     B2_TRY(download(ctx, out, ctx->fb_scaled.p, ob));
     return sync(ctx);
 }
@@ -337,6 +352,26 @@ static int validate_batch(b200timg_ctx *ctx, const b200timg_batch *b) {
     return B200TIMG_OK;
 }
 
+static size_t src_frame_bytes(const b200timg_batch *b) {
+    const int f = b->src_fmt & 0xf;
+    if (f == B200TIMG_FMT_I420 || f == B200TIMG_FMT_NV12) return (size_t)b->src_w * b->src_h + 2 * (size_t)(b->src_w / 2) * (b->src_h / 2);
+    return (size_t)b->src_w * b->src_h * 4;
+}
+
+// scale stage of a batch: the STB-semantics scaler (exact or B200TIMG_FAST_SCALE), the libswscale-style bilinear
+// one (B200TIMG_BILINEAR_SCALE), or colour conversion + bilinear scaling of decoder YUV in one pass
+static int batch_scale(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src, uint8_t *d_fb, int frame_rows,
+                       const ComposeSpec *cs) {
+    const int f = b->src_fmt & 0xf;
+    if (f == B200TIMG_FMT_I420 || f == B200TIMG_FMT_NV12)
+        return launch_yuv_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, frame_rows, b->n_frames);
+    if (f != B200TIMG_FMT_RGBA && f != B200TIMG_FMT_RGB32) return ctx->fail(B200TIMG_EINVAL, "batch: unknown source format %d", b->src_fmt);
+    if (b->flags & B200TIMG_BILINEAR_SCALE)
+        return launch_scale_bilinear(ctx, d_src, b->src_w, b->src_h, f, d_fb, b->out_w, b->out_h, frame_rows, b->n_frames, cs);
+    return launch_scale(ctx, d_src, b->src_w, b->src_h, f, d_fb, b->out_w, b->out_h, frame_rows, b->n_frames, cs,
+                        (b->flags & B200TIMG_FAST_SCALE) != 0);
+}
+
 int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,
                               char *d_out, size_t out_cap, uint64_t *d_offsets) {
     B2_TRY(check_ctx(ctx));
@@ -346,8 +381,7 @@ int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const 
     B2_CUDA(ctx, ctx->fb_scaled.reserve(fb_bytes));
     uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
-    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, b->out_h, b->n_frames, &cs,
-                        (b->flags & B200TIMG_FAST_SCALE) != 0));
+    B2_TRY(batch_scale(ctx, b, d_src, d_fb, b->out_h, &cs));
     if (ctx->ev_after_scale) B2_CUDA(ctx, cudaEventRecord(ctx->ev_after_scale, ctx->stream));
     return launch_blocks(ctx, d_fb, nullptr, b->animation ? 2 : 0, b->out_w, b->out_h, b->n_frames, b->flags,
                          b->x_indent_cells, d_out, out_cap, d_offsets);
@@ -369,8 +403,7 @@ static int sixel_batch_phases(b200timg_ctx *ctx, const b200timg_batch *b, const 
     // src/stb-image-source.cc:56-60); then only the pad strip is cleared and composed, exactly the
     // canvas' own start_row = height call (src/sixel-canvas.cc:115-118).
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
-    B2_TRY(launch_scale(ctx, d_src, b->src_w, b->src_h, b->src_fmt, d_fb, b->out_w, b->out_h, hp, b->n_frames, &cs,
-                        (b->flags & B200TIMG_FAST_SCALE) != 0));
+    B2_TRY(batch_scale(ctx, b, d_src, d_fb, hp, &cs));
     if (ctx->ev_after_scale) B2_CUDA(ctx, cudaEventRecord(ctx->ev_after_scale, ctx->stream));
     if (hp != b->out_h) {
         B2_CUDA(ctx, cudaMemset2DAsync(d_fb + (size_t)b->out_h * b->out_w * 4, frame_bytes, 0,
@@ -425,7 +458,7 @@ static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uin
     B2_TRY(validate_batch(ctx, b));
     if (!src || !out || !offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
     B2_TRY(pipe_init(ctx));
-    const size_t frame_bytes = (size_t)b->src_w * b->src_h * 4;
+    const size_t frame_bytes = src_frame_bytes(b);
     int chunk = (int)std::max<size_t>(1, ((size_t)672 << 20) / frame_bytes);
     if (const char *e = getenv("B200TIMG_CHUNK_FRAMES")) chunk = std::max(1, atoi(e));      // test knob
     if (!sixel && b->animation) chunk = b->n_frames;          // delta frames chain through the whole batch

@@ -76,8 +76,11 @@ yuv420_rgba_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, Y
         }
     }
     {
-        const int x0 = P.ch.first[ox], nx = P.ch.count[ox], y0 = P.cv.first[oy], ny = P.cv.count[oy];
-        const float *hx = P.ch.coeff + (long long)ox * P.ch.widest, *hy = P.cv.coeff + (long long)oy * P.cv.widest;
+        // libswscale's packed-RGB writers (without SWS_FULL_CHR_H_INT, which the reference does not set) carry chroma at
+        // half the OUTPUT width: the two pixels of an output pair share one chroma sample
+        const int cx = ox >> 1;
+        const int x0 = P.ch.first[cx], nx = P.ch.count[cx], y0 = P.cv.first[oy], ny = P.cv.count[oy];
+        const float *hx = P.ch.coeff + (long long)cx * P.ch.widest, *hy = P.cv.coeff + (long long)oy * P.cv.widest;
         for (int j = 0; j < ny; ++j) {
             float au = 0.0f, av = 0.0f;
             if (P.nv12) {
@@ -152,6 +155,18 @@ static void rebase(TriDev *d, const char *base) {
     d->coeff = reinterpret_cast<const float *>(base + reinterpret_cast<size_t>(d->coeff));
 }
 
+// tables are rebuilt only when the geometry changes (a batch pipeline calls the scaler once per chunk)
+static bool tri_cached(b200timg_ctx *ctx, int kind, int iw, int ih, int ow, int oh, void *params, size_t bytes) {
+    const int key[5] = {kind, iw, ih, ow, oh};
+    if (memcmp(key, ctx->tri_key, sizeof key) == 0 && ctx->tri_params.size() == bytes) { memcpy(params, ctx->tri_params.data(), bytes); return true; }
+    return false;
+}
+static void tri_remember(b200timg_ctx *ctx, int kind, int iw, int ih, int ow, int oh, const void *params, size_t bytes) {
+    const int key[5] = {kind, iw, ih, ow, oh};
+    memcpy(ctx->tri_key, key, sizeof key);
+    ctx->tri_params.assign(static_cast<const char *>(params), static_cast<const char *>(params) + bytes);
+}
+
 static int upload_tri(b200timg_ctx *ctx, TriUpload &up) {
     B2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                 // earlier launches may still read the old tables
     B2_CUDA(ctx, ctx->tri_tables.reserve(up.host.size()));
@@ -171,13 +186,23 @@ int launch_yuv_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int
     P.iw = iw; P.ih = ih; P.ow = ow; P.oh = oh; P.out_frame_rows = out_frame_rows;
     P.nv12 = (fmt & 0xf) == B200TIMG_FMT_NV12; P.full_range = (fmt & B200TIMG_FMT_FULL_RANGE) != 0;
     P.frame_bytes = (long long)iw * ih + 2ll * cw * ch;
-    TriAxis yh, yv, chx, cvy;
-    build_tri_axis(iw, ow, &yh); build_tri_axis(ih, oh, &yv); build_tri_axis(cw, ow, &chx); build_tri_axis(ch, oh, &cvy);
-    TriUpload up;
-    up.add(yh, ow, &P.yh); up.add(yv, oh, &P.yv); up.add(chx, ow, &P.ch); up.add(cvy, oh, &P.cv);
-    B2_TRY(upload_tri(ctx, up));
-    const char *base = ctx->tri_tables.as<char>();
-    rebase(&P.yh, base); rebase(&P.yv, base); rebase(&P.ch, base); rebase(&P.cv, base);
+    TriDev td[4];
+    if (!tri_cached(ctx, 1, iw, ih, ow, oh, td, sizeof td)) {
+        TriAxis yh, yv, chx, cvy;
+        build_tri_axis(iw, ow, &yh); build_tri_axis(ih, oh, &yv); build_tri_axis(cw, (ow + 1) / 2, &chx); build_tri_axis(ch, oh, &cvy);
+        if (ow == iw && oh == ih) {              // no scaling: libswscale's unscaled yuv2rgb path replicates chroma rows (2x2 blocks share a sample)
+            cvy.widest = 1; cvy.coeff.assign((size_t)oh, 1.0f);
+            for (int y = 0; y < oh; ++y) { cvy.first[y] = y >> 1; cvy.count[y] = 1; }
+        }
+        TriUpload up;
+        up.add(yh, ow, &td[0]); up.add(yv, oh, &td[1]); up.add(chx, (ow + 1) / 2, &td[2]); up.add(cvy, oh, &td[3]);
+        ctx->tri_key[0] = 0;
+        B2_TRY(upload_tri(ctx, up));
+        const char *base = ctx->tri_tables.as<char>();
+        for (auto &t : td) rebase(&t, base);
+        tri_remember(ctx, 1, iw, ih, ow, oh, td, sizeof td);
+    }
+    P.yh = td[0]; P.yv = td[1]; P.ch = td[2]; P.cv = td[3];
     B2_KERNEL(ctx, "yuv420_rgba_kernel");
     yuv420_rgba_kernel<<<dim3((ow + 31) / 32, (oh + 7) / 8, n_frames), 256, 0, ctx->stream>>>(d_in, reinterpret_cast<uint32_t *>(d_out), P);
     B2_LAUNCH_CHECK(ctx);
@@ -191,13 +216,19 @@ int launch_scale_bilinear(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih
     BilinearParams P;
     P.iw = iw; P.ih = ih; P.ow = ow; P.oh = oh; P.out_frame_rows = out_frame_rows; P.bgra = fmt == B200TIMG_FMT_RGB32;
     if (cs) P.cs = *cs; else { memset(&P.cs, 0, sizeof P.cs); P.cs.pw = P.cs.ph = 1; }
-    TriAxis h, v;
-    build_tri_axis(iw, ow, &h); build_tri_axis(ih, oh, &v);
-    TriUpload up;
-    up.add(h, ow, &P.h); up.add(v, oh, &P.v);
-    B2_TRY(upload_tri(ctx, up));
-    const char *base = ctx->tri_tables.as<char>();
-    rebase(&P.h, base); rebase(&P.v, base);
+    TriDev td[2];
+    if (!tri_cached(ctx, 2, iw, ih, ow, oh, td, sizeof td)) {
+        TriAxis h, v;
+        build_tri_axis(iw, ow, &h); build_tri_axis(ih, oh, &v);
+        TriUpload up;
+        up.add(h, ow, &td[0]); up.add(v, oh, &td[1]);
+        ctx->tri_key[0] = 0;
+        B2_TRY(upload_tri(ctx, up));
+        const char *base = ctx->tri_tables.as<char>();
+        for (auto &t : td) rebase(&t, base);
+        tri_remember(ctx, 2, iw, ih, ow, oh, td, sizeof td);
+    }
+    P.h = td[0]; P.v = td[1];
     B2_KERNEL(ctx, "bilinear_rgba_kernel");
     bilinear_rgba_kernel<<<dim3((ow + 31) / 32, (oh + 7) / 8, n_frames), 256, 0, ctx->stream>>>(
         reinterpret_cast<const uint32_t *>(d_in), reinterpret_cast<uint32_t *>(d_out), P);

@@ -79,6 +79,9 @@ struct b200timg_ctx {
     b200timg::DevBuf tables;       // resampler coefficient tables
     b200timg::DevBuf sixel_work;   // palettes, LUTs, index planes, band tables
     b200timg::DevBuf misc;         // small flags / sizes
+    b200timg::DevBuf tri_tables;   // bilinear / YUV scaler tap tables ...
+    int tri_key[5] = {0, 0, 0, 0, 0};          // ... for this (kind, iw, ih, ow, oh), device pointers cached in tri_params
+    std::vector<char> tri_params;
     b200timg::DevBuf scale_list;   // work list of tiles the opaque-only scaler hands to the general one
     b200timg::HostBuf pinned;      // staging for sizes / offsets
     b200timg::HostBuf pinned_io;   // staging for pageable payloads
@@ -211,6 +214,11 @@ int launch_blocks(b200timg_ctx *ctx, const uint8_t *d_fb, const uint8_t *d_prev,
 // fast != 0: the <= 1 LSB arithmetic (FMA, no 1/255 round trip) where a kernel offers it; 0: bit-exact.
 int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out,
                  int ow, int oh, int out_frame_rows, int n_frames, const ComposeSpec *cs = nullptr, int fast = 0);
+// libswscale-style bilinear (triangle) scalers, bilinear.cu: RGBA -> RGBA and YUV 4:2:0 -> RGBA
+int launch_scale_bilinear(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out, int ow, int oh,
+                          int out_frame_rows, int n_frames, const ComposeSpec *cs);
+int launch_yuv_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt, uint8_t *d_out, int ow, int oh,
+                     int out_frame_rows, int n_frames);
 int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
                  size_t out_cap, uint64_t *d_offsets, int phases);
 int sixel_debug_fetch(b200timg_ctx *ctx, uint32_t *h_palette, uint32_t *h_counts, uint8_t *h_index, size_t index_bytes);

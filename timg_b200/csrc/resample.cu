@@ -880,13 +880,13 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     if (tid < V3_TW) {
         const int ox = ox0 + tid;
         const bool ok = ox < P.ow;
-        s_hfirst[tid] = ok ? P.h_first[ox] - ix0 : 0;
+        s_hfirst[tid] = P.h_first[min(ox, P.ow - 1)] - ix0;       // columns past the image edge repeat the last one (zero weights): the walk stays monotone
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_hc[tid * 8 + i] = (ok && i < P.h_widest) ? P.h_coeff[(long long)ox * P.h_widest + i] : 0.0f;
     } else if (tid < V3_TW + V3_TH) {
         const int t = tid - V3_TW, oy = oy0 + t;
         const bool ok = oy < P.oh;
-        s_vfirst[t] = ok ? P.v_first[oy] - iy0 : 0;
+        s_vfirst[t] = P.v_first[min(oy, P.oh - 1)] - iy0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_vc[t * 8 + i] = (ok && i < P.v_widest) ? P.v_coeff[(long long)oy * P.v_widest + i] : 0.0f;
     }
@@ -913,36 +913,57 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
         return;
     }
     const uint32_t sel_r = 0x7540u | (P.bgra ? 2u : 0u), sel_g = 0x7541u, sel_b = 0x7540u | (P.bgra ? 0u : 2u);
-    // ---- vertical: T[ty][2cp .. 2cp+1] = sum_k S[vfirst[ty] + k][..] * vc[ty][k], rows in order
+    // ---- vertical, streaming: a thread owns two neighbouring columns and 8 consecutive output rows.  It walks down
+    // the input rows those outputs need ONCE: each row is loaded and converted once into a VC-deep register window
+    // (slot = row mod VC, static because the walk is unrolled by VC), and an output row is produced the moment its
+    // last tap arrives -- its taps are then exactly the window, oldest first.  Loads and byte->float conversions per
+    // intermediate pixel drop from VC to ~1.4 (input rows per output row, plus the window warm-up of each group).
     const int ncp = sp >> 1;
+    {
+        const int j0 = (wid >> 1) * 8, j1 = j0 + 8;
+        const int f0 = s_vfirst[j0], rend = s_vfirst[j1 - 1] + VC;            // input rows [f0, rend) of the window
+        for (int cp = (wid & 1) * 32 + lane; cp < ncp; cp += 64) {
+            F2 w0[VC], w1[VC], wb[VC];
+            int j = j0, ej = f0 + VC - 1;                                      // next output row and its last input row
+            const uint32_t *scol = S + 2 * cp;
 #pragma unroll 1
-    for (int r = 0; r < V3_TH / 8; ++r) {
-        const int ty = wid + 8 * r;
-        const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + ty * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + ty * 8 + 4);
-        const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        const uint32_t *srow = S + s_vfirst[ty] * sp;
-        for (int cp = lane; cp < ncp; cp += 32) {
-            F2 a0, a1, ab;
+            for (int r0 = f0; r0 < rend; r0 += VC) {
 #pragma unroll
-            for (int k = 0; k < VC; ++k) {
-                const uint2 pp = *reinterpret_cast<const uint2 *>(srow + k * sp + 2 * cp);
-                const F2 p0 = {byte_val<EXACT>(pp.x, sel_r), byte_val<EXACT>(pp.x, sel_g)};
-                const F2 p1 = {byte_val<EXACT>(pp.y, sel_r), byte_val<EXACT>(pp.y, sel_g)};
-                const F2 pb = {byte_val<EXACT>(pp.x, sel_b), byte_val<EXACT>(pp.y, sel_b)};
-                if (k == 0) { a0 = f2_mul<EXACT>(p0, vc[0]); a1 = f2_mul<EXACT>(p1, vc[0]); ab = f2_mul<EXACT>(pb, vc[0]); }
-                else { a0 = f2_mac<EXACT>(a0, p0, vc[k]); a1 = f2_mac<EXACT>(a1, p1, vc[k]); ab = f2_mac<EXACT>(ab, pb, vc[k]); }
+                for (int sl = 0; sl < VC; ++sl) {
+                    const int r = r0 + sl;
+                    if (r < rend) {
+                        const uint2 pp = *reinterpret_cast<const uint2 *>(scol + r * sp);
+                        w0[sl] = F2{byte_val<EXACT>(pp.x, sel_r), byte_val<EXACT>(pp.x, sel_g)};
+                        w1[sl] = F2{byte_val<EXACT>(pp.y, sel_r), byte_val<EXACT>(pp.y, sel_g)};
+                        wb[sl] = F2{byte_val<EXACT>(pp.x, sel_b), byte_val<EXACT>(pp.y, sel_b)};
+                        while (j < j1 && ej == r) {                           // uniform: every thread walks the same rows
+                            const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + j * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + j * 8 + 4);
+                            const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                            F2 a0 = f2_mul<EXACT>(w0[(sl + 1) % VC], vc[0]), a1 = f2_mul<EXACT>(w1[(sl + 1) % VC], vc[0]);
+                            F2 ab = f2_mul<EXACT>(wb[(sl + 1) % VC], vc[0]);
+#pragma unroll
+                            for (int k = 1; k < VC; ++k) {
+                                a0 = f2_mac<EXACT>(a0, w0[(sl + 1 + k) % VC], vc[k]);
+                                a1 = f2_mac<EXACT>(a1, w1[(sl + 1 + k) % VC], vc[k]);
+                                ab = f2_mac<EXACT>(ab, wb[(sl + 1 + k) % VC], vc[k]);
+                            }
+                            float2 *t = TRG + j * tp + 2 * cp;
+                            t[0] = make_float2(a0.x, a0.y); t[1] = make_float2(a1.x, a1.y);
+                            float *tb = TB + j * tp + 2 * cp;
+                            tb[0] = ab.x; tb[1] = ab.y;
+                            ++j;
+                            ej = j < j1 ? s_vfirst[j] + VC - 1 : -1;
+                        }
+                    }
+                }
             }
-            float2 *t = TRG + ty * tp + 2 * cp;
-            t[0] = make_float2(a0.x, a0.y); t[1] = make_float2(a1.x, a1.y);
-            float *tb = TB + ty * tp + 2 * cp;
-            tb[0] = ab.x; tb[1] = ab.y;
         }
     }
     __syncthreads();
-    // ---- horizontal: lane = output row, the warp's column changes with j; taps and start index are warp-uniform
+    // ---- horizontal, streaming the same way along x: lane = output row, a warp owns 8 consecutive output columns
+    // and walks the intermediate columns they need once (window of HC columns in registers).  Pixels go straight
+    // into the transpose buffer O (it aliases S, which is dead now).
     const bool hseq = P.h_sequential != 0;
-    const float2 *trow = TRG + lane * tp;
-    const float *brow = TB + lane * tp;
     float av = 0.0f;                                              // EXACT: vertical tap sum of an all-ones (alpha) column
     if (EXACT) {
         const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + lane * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + lane * 8 + 4);
@@ -951,52 +972,68 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
 #pragma unroll
         for (int k = 1; k < VC; ++k) av = fadd(av, vc[k]);
     }
-    uint32_t px[V3_TW / 8];
+    {
+        const int tx0 = wid * 8, tx1 = tx0 + 8;
+        const int f0 = s_hfirst[tx0], cend = s_hfirst[tx1 - 1] + HC;
+        const float2 *trow = TRG + lane * tp;
+        const float *brow = TB + lane * tp;
+        F2 wrg[HC]; float wbb[HC];
+        int tx = tx0, etx = f0 + HC - 1;
+#pragma unroll 1
+        for (int c0 = f0; c0 < cend; c0 += HC) {
 #pragma unroll
-    for (int j = 0; j < V3_TW / 8; ++j) {
-        const int tx = wid + 8 * j;
-        const float4 h0 = *reinterpret_cast<const float4 *>(s_hc + tx * 8), h1 = *reinterpret_cast<const float4 *>(s_hc + tx * 8 + 4);
-        const float hc[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        const float2 *rg = trow + s_hfirst[tx];
-        const float *bb = brow + s_hfirst[tx];
-        F2 c2; float cb, al = 1.0f;
-        if (hseq) {
-            F2 a = f2_mul<EXACT>(F2{rg[0].x, rg[0].y}, hc[0]);
-            float b = EXACT ? fmul(bb[0], hc[0]) : bb[0] * hc[0];
-            float aa = EXACT ? fmul(av, hc[0]) : 0.0f;
+            for (int sl = 0; sl < HC; ++sl) {
+                const int c = c0 + sl;
+                if (c < cend) {
+                    const float2 q = trow[c];
+                    wrg[sl] = F2{q.x, q.y}; wbb[sl] = brow[c];
+                    while (tx < tx1 && etx == c) {
+                        const float4 h0 = *reinterpret_cast<const float4 *>(s_hc + tx * 8), h1 = *reinterpret_cast<const float4 *>(s_hc + tx * 8 + 4);
+                        const float hc[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                        F2 c2; float cb, al = 1.0f;
+                        if (hseq) {
+                            F2 a = f2_mul<EXACT>(wrg[(sl + 1) % HC], hc[0]);
+                            float b = EXACT ? fmul(wbb[(sl + 1) % HC], hc[0]) : wbb[(sl + 1) % HC] * hc[0];
+                            float aa = EXACT ? fmul(av, hc[0]) : 0.0f;
 #pragma unroll
-            for (int i = 1; i < (HC < 3 ? HC : 3); ++i) {
-                a = f2_mac<EXACT>(a, F2{rg[i].x, rg[i].y}, hc[i]); b = f1_mac<EXACT>(b, bb[i], hc[i]);
-                if (EXACT) aa = fadd(aa, fmul(av, hc[i]));
+                            for (int i = 1; i < (HC < 3 ? HC : 3); ++i) {
+                                a = f2_mac<EXACT>(a, wrg[(sl + 1 + i) % HC], hc[i]); b = f1_mac<EXACT>(b, wbb[(sl + 1 + i) % HC], hc[i]);
+                                if (EXACT) aa = fadd(aa, fmul(av, hc[i]));
+                            }
+                            c2 = a; cb = b; if (EXACT) al = aa;
+                        } else {
+                            F2 a0 = f2_mul<EXACT>(wrg[(sl + 1) % HC], hc[0]), a1 = f2_mul<EXACT>(wrg[(sl + 2) % HC], hc[1]);
+                            float b0 = EXACT ? fmul(wbb[(sl + 1) % HC], hc[0]) : wbb[(sl + 1) % HC] * hc[0];
+                            float b1 = EXACT ? fmul(wbb[(sl + 2) % HC], hc[1]) : wbb[(sl + 2) % HC] * hc[1];
+                            float l0 = EXACT ? fmul(av, hc[0]) : 0.0f, l1 = EXACT ? fmul(av, hc[1]) : 0.0f;
+#pragma unroll
+                            for (int i = 2; i < HC; ++i) {
+                                if (i & 1) { a1 = f2_mac<EXACT>(a1, wrg[(sl + 1 + i) % HC], hc[i]); b1 = f1_mac<EXACT>(b1, wbb[(sl + 1 + i) % HC], hc[i]); if (EXACT) l1 = fadd(l1, fmul(av, hc[i])); }
+                                else { a0 = f2_mac<EXACT>(a0, wrg[(sl + 1 + i) % HC], hc[i]); b0 = f1_mac<EXACT>(b0, wbb[(sl + 1 + i) % HC], hc[i]); if (EXACT) l0 = fadd(l0, fmul(av, hc[i])); }
+                            }
+                            c2 = EXACT ? f2_add(a0, a1) : F2{a0.x + a1.x, a0.y + a1.y};
+                            cb = EXACT ? fadd(b0, b1) : b0 + b1;
+                            if (EXACT) al = fadd(l0, l1);
+                        }
+                        uint32_t px;
+                        if (EXACT) {
+                            float v[7];
+                            v[0] = c2.x; v[1] = c2.y; v[2] = cb; v[3] = al; v[4] = c2.x; v[5] = c2.y; v[6] = cb;
+                            px = compose_at(P.cs, encode_px(v), ox0 + tx, oy0 + lane);
+                        } else {
+                            const uint32_t r8 = __float2uint_rz(fminf(fmaxf(c2.x + 0.5f, 0.0f), 255.0f));
+                            const uint32_t g8 = __float2uint_rz(fminf(fmaxf(c2.y + 0.5f, 0.0f), 255.0f));
+                            const uint32_t b8 = __float2uint_rz(fminf(fmaxf(cb + 0.5f, 0.0f), 255.0f));
+                            px = pack_rgba(r8, g8, b8, 0xffu);                    // opaque in, opaque out: nothing to compose
+                        }
+                        O[lane * (V3_TW + 1) + tx] = px;
+                        ++tx;
+                        etx = tx < tx1 ? s_hfirst[tx] + HC - 1 : -1;
+                    }
+                }
             }
-            c2 = a; cb = b; if (EXACT) al = aa;
-        } else {
-            F2 a0 = f2_mul<EXACT>(F2{rg[0].x, rg[0].y}, hc[0]), a1 = f2_mul<EXACT>(F2{rg[1].x, rg[1].y}, hc[1]);
-            float b0 = EXACT ? fmul(bb[0], hc[0]) : bb[0] * hc[0], b1 = EXACT ? fmul(bb[1], hc[1]) : bb[1] * hc[1];
-            float l0 = EXACT ? fmul(av, hc[0]) : 0.0f, l1 = EXACT ? fmul(av, hc[1]) : 0.0f;
-#pragma unroll
-            for (int i = 2; i < HC; ++i) {
-                if (i & 1) { a1 = f2_mac<EXACT>(a1, F2{rg[i].x, rg[i].y}, hc[i]); b1 = f1_mac<EXACT>(b1, bb[i], hc[i]); if (EXACT) l1 = fadd(l1, fmul(av, hc[i])); }
-                else { a0 = f2_mac<EXACT>(a0, F2{rg[i].x, rg[i].y}, hc[i]); b0 = f1_mac<EXACT>(b0, bb[i], hc[i]); if (EXACT) l0 = fadd(l0, fmul(av, hc[i])); }
-            }
-            c2 = EXACT ? f2_add(a0, a1) : F2{a0.x + a1.x, a0.y + a1.y};
-            cb = EXACT ? fadd(b0, b1) : b0 + b1;
-            if (EXACT) al = fadd(l0, l1);
-        }
-        if (EXACT) {
-            float v[7];
-            v[0] = c2.x; v[1] = c2.y; v[2] = cb; v[3] = al; v[4] = c2.x; v[5] = c2.y; v[6] = cb;
-            px[j] = compose_at(P.cs, encode_px(v), ox0 + tx, oy0 + lane);
-        } else {
-            const uint32_t r8 = __float2uint_rz(fminf(fmaxf(c2.x + 0.5f, 0.0f), 255.0f));
-            const uint32_t g8 = __float2uint_rz(fminf(fmaxf(c2.y + 0.5f, 0.0f), 255.0f));
-            const uint32_t b8 = __float2uint_rz(fminf(fmaxf(cb + 0.5f, 0.0f), 255.0f));
-            px[j] = pack_rgba(r8, g8, b8, 0xffu);                     // opaque in, opaque out: nothing to compose
         }
     }
-    __syncthreads();                                              // every warp is done reading T (O aliases S, which died earlier, but keep the order simple)
-#pragma unroll
-    for (int j = 0; j < V3_TW / 8; ++j) O[lane * (V3_TW + 1) + wid + 8 * j] = px[j];
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < V3_TH / 8; ++i) {

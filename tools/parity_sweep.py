@@ -15,6 +15,9 @@ seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 n_scale = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 n_sixel = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 rng = np.random.default_rng(seed)
+if os.environ.get("B200TIMG_CUSIM"):          # developer aid: run the sweep on the CPU simulator of the kernels
+    from tools import cusim
+    cusim.activate()
 ctx = timg_b200.Context(0)
 bad = 0
 kernels = {}
