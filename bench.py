@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--yuv", action="store_true",
                     help="feed decoder-style I420 frames (1.5 B/px) through the fused colour-conversion + bilinear scaler "
                          "(the video source's sws_scale, src/video-source.cc:352-354) instead of RGBA through ImageScaler")
+    ap.add_argument("--py-gather", action="store_true",
+                    help="N>1: gather through torch.distributed point-to-point (round 1) instead of the C-ABI b200timg_gather")
     ap.add_argument("--exact-scale", action="store_true",
                     help="bit-exact scaler arithmetic on the sixel path instead of the <= 1 LSB fused-multiply-add mode")
     args = ap.parse_args()
@@ -249,6 +251,8 @@ def main():
         return
 
     numa = pin_to_gpu_numa(local_rank)
+    if world > 1:      # intra-node point-to-point through the copy engines: the gather then takes no SMs from rank 0's kernels
+        os.environ.setdefault("NCCL_P2P_USE_CUDA_MEMCPY", "1")
     import torch
     import torch.distributed as dist
     import timg_b200
@@ -319,15 +323,23 @@ def main():
         if rc != 0:
             raise RuntimeError(L.b200timg_last_error(ctx.h).decode())
         if world > 1 and gather:
-            pending[i] = shard.gather_encoded_async(outs[i], offss[i], dst=0)
+            pending[i] = abi_gather.start(outs[i], offss[i]) if abi_gather else shard.gather_encoded_async(outs[i], offss[i], dst=0)
 
     # first call sizes the output; grow the buffers if the guess was too small (nothing is written past cap)
+    abi_gather = None
     step(gather=False)
     torch.cuda.synchronize(dev)
     total = int(offss[0][-1].item())
-    if total > cap:
-        cap = int(total * 1.05)
+    slot = 0
+    if world > 1:          # one slot size for all ranks: the largest batch + 2 %
+        tmax = torch.tensor([total], dtype=torch.int64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        slot = (int(tmax.item()) * 102 // 100 + 4095) // 4096 * 4096
+    if total > cap or slot > cap:
+        cap = max(int(total * 1.05), slot)
         outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    if world > 1 and not args.py_gather:
+        abi_gather = shard.AbiGather(ctx, F, slot, root=0, buffers=nbuf)
     for _ in range(args.warmup):
         step()
     drain()
@@ -469,7 +481,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mpx/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
-                "config": dict(config, parallelism=f"frames sharded x{world}, NCCL gather of encoded bytes to rank 0; "
+                "config": dict(config, parallelism=f"frames sharded x{world}, NCCL gather of encoded bytes to rank 0 "
+                               f"({'torch.distributed p2p' if args.py_gather else 'b200timg_gather, fixed slots, no host sync'}); "
                                "double-buffered output: the gather of batch k overlaps the kernels of batch k+1"
                                if world > 1 else "1 GPU",
                                scaler="exact" if (args.exact_scale or not sixel) else "fast (<= 1 LSB, B200TIMG_FAST_SCALE)"),

@@ -226,6 +226,29 @@ int b200timg_resample_plan(int in_w, int in_h, int out_w, int out_h, int axis, i
                            int *flags, int32_t *first, int32_t *count, int32_t *lead,
                            float *coeff, size_t coeff_cap);
 
+/* ======================= K7: gather of the encoded frames over NCCL ==============================
+ * One process per GPU.  The reference is a single process and has no counterpart; frames are
+ * independent units, every rank encodes its own batch (b200timg_*_batch_dev) and this call moves the
+ * encoded bytes to `root`.  Fixed-slot protocol without any host synchronisation: every rank passes the same
+ * slot_bytes (>= the size of any rank's batch, <= the capacity of d_payload); on root, rank r's bytes land at
+ * d_dst + r*slot_bytes and frame i of rank r is
+ *     [d_dst_offsets[r*(n_frames+1) + i], d_dst_offsets[r*(n_frames+1) + i + 1])   (absolute, inside d_dst).
+ * d_dst: nranks*slot_bytes bytes, d_dst_offsets: nranks*(n_frames+1) entries, both only read on root.
+ * *d_status (optional, root): bit r set if rank r's batch did not fit its slot (its frames are then truncated
+ * at the slot end, nothing is read or written out of bounds).  The transfer runs on the context's gather
+ * stream behind the compute stream, so the next batch's kernels overlap it.  b200timg_gather returns a ticket
+ * (>= 0) or a negative error; b200timg_gather_wait(ctx, ticket, block_host) orders the compute stream (or the
+ * host) after that gather -- call it before consuming d_dst or overwriting d_payload.  The last four gathers
+ * can be waited for individually (double-buffered callers wait for the one that used the buffer they reuse). */
+#define B200TIMG_NCCL_ID_BYTES 128
+int  b200timg_gather_unique_id(char id[B200TIMG_NCCL_ID_BYTES]);            /* ncclGetUniqueId; share it with all ranks */
+int  b200timg_gather_init(b200timg_ctx *ctx, const char id[B200TIMG_NCCL_ID_BYTES], int rank, int nranks);   /* ncclCommInitRank */
+int  b200timg_gather_attach(b200timg_ctx *ctx, void *nccl_comm, int rank, int nranks);  /* use the caller's ncclComm_t */
+void b200timg_gather_shutdown(b200timg_ctx *ctx);
+int  b200timg_gather(b200timg_ctx *ctx, const char *d_payload, const uint64_t *d_offsets, int n_frames,
+                     size_t slot_bytes, char *d_dst, uint64_t *d_dst_offsets, uint32_t *d_status, int root);
+int  b200timg_gather_wait(b200timg_ctx *ctx, int ticket, int block_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,8 +16,14 @@ from timg_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-DE_BETWEEN = 3.0     # stated tolerance: device vs libsixel-faithful restatement (blurred mean delta-E)
-DE_SOURCE = 0.5      # stated tolerance: |error vs source (device) - error vs source (restatement)|
+DE_BETWEEN = 3.0     # stated tolerance: device vs libsixel-faithful restatement (mean delta-E after a 5x5 box blur)
+DE_SOURCE = 0.5      # stated tolerance: |error vs source (device) - error vs source (restatement)|, blurred
+# The same WITHOUT the blur.  The two order-free substitutions (sixel.cu header) change the palette (tie order in
+# the median cut) and with it nearly every pixel's index: measured 90-98 % of the pixels decode to a different
+# colour than the libsixel-faithful restatement's, mean delta-E between the two images 6-12 (two different dither
+# patterns of the same picture).  What is preserved is the quality: the error against the SOURCE is the same.
+DE_SOURCE_UNBLURRED = 1.5    # |mean dE(device, source) - mean dE(restatement, source)|, no blur (measured 0.05-1.05)
+DE_BETWEEN_UNBLURRED = 14.0  # mean dE(device, restatement), no blur (measured 6.4-12.2; informational upper bound)
 
 
 def pct(pal):
@@ -53,6 +59,25 @@ def test_sixel_cuda_within_tolerance_of_libsixel_semantics(ctx, kind, w, h):
     src = fb[..., :3]
     assert oracle.mean_delta_e(got, ref, 2) < DE_BETWEEN
     assert abs(oracle.mean_delta_e(got, src, 2) - oracle.mean_delta_e(ref, src, 2)) < DE_SOURCE
+    assert abs(oracle.mean_delta_e(got, src, 0) - oracle.mean_delta_e(ref, src, 0)) < DE_SOURCE_UNBLURRED
+    assert oracle.mean_delta_e(got, ref, 0) < DE_BETWEEN_UNBLURRED
+
+
+def test_sixel_cuda_against_real_libsixel_if_the_host_has_it(ctx):
+    """SURVEY 8c acceptance item 4: libsixel is not in the reference tree or the image, but if this host has one
+    (find_library / pkg-config), the device stream is compared with the real library run through the reference's
+    exact call sequence (oracle/libsixel_probe.py).  Skipped, with the probe's log as the reason, otherwise."""
+    from oracle import libsixel_probe
+    lib, how = libsixel_probe.find()
+    if lib is None:
+        pytest.skip("no libsixel on this host: " + how)
+    for kind, w, h in [("photo", 337, 192), ("noise", 200, 96)]:
+        fb = synth.frame_np(1234, w, h, kind)
+        got, _ = oracle.sixel_decode(ctx.sixel_encode(fb))
+        ref, _ = oracle.sixel_decode(libsixel_probe.encode(fb))
+        src = fb[..., :3]
+        assert oracle.mean_delta_e(got, ref, 2) < DE_BETWEEN
+        assert abs(oracle.mean_delta_e(got, src, 0) - oracle.mean_delta_e(ref, src, 0)) < DE_SOURCE_UNBLURRED
 
 
 def test_sixel_cuda_few_colours_no_dither(ctx):

@@ -72,6 +72,13 @@ ABI = {
                                        C.c_uint32, C.c_int, C.c_int, C.c_int]),
     "b200timg_sixel_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                      C.c_void_p]),
+    "b200timg_gather_unique_id": (C.c_int, [C.c_char_p]),
+    "b200timg_gather_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "b200timg_gather_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "b200timg_gather_shutdown": (None, [C.c_void_p]),
+    "b200timg_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int]),
+    "b200timg_gather_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "b200timg_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "b200timg_profile_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "b200timg_sixel_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

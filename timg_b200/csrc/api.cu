@@ -67,6 +67,8 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    b200timg_gather_shutdown(ctx);
+    ctx->gather_status.release();
     ctx->in_stage.release(); ctx->fb_scaled.release(); ctx->prev_stage.release();
     ctx->out_stage.release(); ctx->offsets.release(); ctx->cells.release(); ctx->rows.release();
     ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release(); ctx->scale_list.release(); ctx->tri_tables.release();

@@ -92,6 +92,14 @@ struct b200timg_ctx {
     b200timg::DevBuf pipe_in[2], pipe_out[2];
     bool pipe_ready = false;
     bool sixel_attrs_set = false;            // cudaFuncSetAttribute done for this context's device
+    // K7 gather (gather.cu): NCCL communicator (owned or attached), its stream and ordering events
+    void *nccl_comm = nullptr;
+    bool nccl_owned = false;
+    int nccl_rank = 0, nccl_nranks = 1;
+    cudaStream_t gather_stream = nullptr;
+    cudaEvent_t ev_gather_ready = nullptr, ev_gather_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t gather_seq = 0;
+    b200timg::DevBuf gather_status;
 
     int fail(int code, const char *fmt, ...) {
         va_list ap; va_start(ap, fmt);

@@ -85,3 +85,56 @@ def gather_encoded_async(payload, offsets, dst=0, group=None):
 def gather_encoded(payload, offsets, dst=0, group=None):
     """gather_encoded_async(...).wait(): see there."""
     return gather_encoded_async(payload, offsets, dst, group).wait()
+
+
+class AbiGather:
+    """The C-ABI gather (b200timg_gather, timg_b200/csrc/gather.cu) driven from Python: NCCL communicator created
+    inside the library, fixed slots, no host synchronisation per gather.  torch.distributed is used once, to hand
+    rank 0's ncclUniqueId to the other ranks."""
+
+    class _Ticket:
+        def __init__(self, owner, ticket, dst, dst_offsets):
+            self.owner, self.ticket, self.dst, self.dst_offsets = owner, ticket, dst, dst_offsets
+
+        def wait(self, block_host=False):
+            """Order the compute stream (or, with block_host, the host) after this gather.  On the root returns
+            (bytes of all ranks in fixed slots, absolute offsets [world * (n + 1)]), else (None, None)."""
+            self.owner._chk(self.owner.L.b200timg_gather_wait(self.owner.ctx.h, self.ticket, int(block_host)))
+            return self.dst, self.dst_offsets
+
+    def __init__(self, ctx, n_frames, slot_bytes, root=0, group=None, buffers=2):
+        import ctypes as C
+        import timg_b200
+        self.L, self.ctx, self.n, self.slot, self.root = timg_b200.lib(), ctx, n_frames, int(slot_bytes), root
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ident = C.create_string_buffer(128)
+        if self.rank == root:
+            self._chk(self.L.b200timg_gather_unique_id(ident))
+        box = [ident.raw]
+        dist.broadcast_object_list(box, src=root, group=group)
+        self._chk(self.L.b200timg_gather_init(ctx.h, box[0], self.rank, self.world))
+        dev = torch.device("cuda", ctx.device)
+        self.k, self.dsts, self.dst_offs = 0, [], []
+        if self.rank == root:
+            self.dsts = [torch.empty(self.world * self.slot, dtype=torch.uint8, device=dev) for _ in range(buffers)]
+            self.dst_offs = [torch.zeros(self.world * (n_frames + 1), dtype=torch.int64, device=dev) for _ in range(buffers)]
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.dst = self.dst_offsets = None
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise RuntimeError(self.L.b200timg_last_error(self.ctx.h).decode())
+
+    def start(self, payload, offsets):
+        """payload: uint8 cuda tensor with >= slot_bytes capacity; offsets: int64/uint64 [n+1] on the same device."""
+        i = self.k % max(1, len(self.dsts)) if self.dsts else 0
+        self.k += 1
+        if self.rank == self.root:
+            self.dst, self.dst_offsets = self.dsts[i], self.dst_offs[i]
+            rc = self.L.b200timg_gather(self.ctx.h, payload.data_ptr(), offsets.data_ptr(), self.n, self.slot,
+                                        self.dst.data_ptr(), self.dst_offsets.data_ptr(), self.status.data_ptr(), self.root)
+        else:
+            rc = self.L.b200timg_gather(self.ctx.h, payload.data_ptr(), offsets.data_ptr(), self.n, self.slot, None, None, None,
+                                        self.root)
+        self._chk(rc)
+        return AbiGather._Ticket(self, rc, self.dst, self.dst_offsets)
