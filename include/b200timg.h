@@ -171,7 +171,11 @@ typedef struct {
     int flags;                  /* B200TIMG_QUARTER | _UPPER | _COLOR8 */
     int x_indent_cells;
     int animation;              /* 1: frame f>0 is delta-encoded against frame f-1
-                                   (Send with dy == -height, :344-346); frame 0 is full */
+                                   (Send with dy == -height, :344-346); frame 0 is full.
+                                   2: the same, but frame 0 is a HALO -- scaled and used as frame 1's
+                                   predecessor, never emitted (offsets[0] == offsets[1]).  A rank that owns
+                                   frames [lo, hi) of a sharded animation passes frames [lo-1, hi) this way
+                                   and produces exactly the bytes an unsharded run produces for lo..hi-1. */
 } b200timg_batch;
 
 /* Device-resident variants: d_src, d_out, d_offsets are DEVICE pointers; nothing crosses

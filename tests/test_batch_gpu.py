@@ -35,8 +35,12 @@ def test_blocks_batch_c3_shape_matches_oracle(ctx, chunk, monkeypatch):
         assert outs[f] == oracle.BlockCanvas(True).send(fb, x=6), f
 
 
-def test_blocks_batch_animation_delta_matches_canvas_sequence(ctx):
-    """animation=1: frame f is delta-encoded against frame f-1, as a canvas receiving Send(dy=-h)."""
+@pytest.mark.parametrize("chunk", [None, "2", "1", "4"])
+def test_blocks_batch_animation_delta_matches_canvas_sequence(ctx, chunk, monkeypatch):
+    """animation=1: frame f is delta-encoded against frame f-1, as a canvas receiving Send(dy=-h); the host pipeline
+    may cut the animation into chunks (each later chunk re-uploads one halo frame)."""
+    if chunk:
+        monkeypatch.setenv("B200TIMG_CHUNK_FRAMES", chunk)
     n, w, h = 6, 128, 64
     frames = []
     for k in range(n):
@@ -62,6 +66,30 @@ def test_sixel_batch_chunked_equals_single_frames(ctx, chunk, monkeypatch):
     for f in range(n):
         fbs = ctx.scale(frames[f], ow, oh)
         assert outs[f] == ctx.sixel_encode(fbs), f
+
+
+def test_blocks_animation_sharded_with_halo_frames_equals_unsharded(ctx):
+    """a rank that owns frames [lo, hi) of a delta-encoded animation loads the halo frame lo-1 and encodes
+    with animation = 2; the concatenation over ranks is byte-identical to the unsharded run."""
+    from timg_b200 import shard
+    n, w, h = 11, 128, 64
+    frames = []
+    for k in range(n):
+        fr = synth.frame_np(70, w, h, "photo")
+        fr[4 + 3 * k:12 + 3 * k, 10 + 9 * k:18 + 9 * k] = synth.frame_np(80 + k, 8, 8, "noise")
+        frames.append(fr)
+    frames = np.stack(frames)
+    whole = ctx.blocks_batch(frames, _batch(n, w, h, w, h, flags=timg_b200.QUARTER, animation=1))
+    for world in (2, 3, 4):
+        got = []
+        for r in range(world):
+            first, cnt, anim = shard.animation_chunk(n, r, world)
+            outs = ctx.blocks_batch(frames[first:first + cnt], _batch(cnt, w, h, w, h, flags=timg_b200.QUARTER, animation=anim))
+            if anim == 2:
+                assert outs[0] == b""
+                outs = outs[1:]
+            got += outs
+        assert got == whole, world
 
 
 def test_sixel_batch_too_small_buffer_reports_enospc(ctx):

@@ -111,3 +111,20 @@ def test_two_rank_async_gathers_in_flight():
         p.join(120)
         assert p.exitcode == 0
     assert list(ok) == [3, 3]
+
+
+def test_animation_chunks_cover_the_sequence_with_one_halo_frame():
+    """Delta animations: every rank but the first loads exactly one halo frame and the chunks tile [0, n)."""
+    from timg_b200 import shard
+    for n in (1, 2, 7, 300, 10000):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                first, cnt, anim = shard.animation_chunk(n, r, world)
+                lo, hi = shard.shard_range(n, r, world)
+                if hi <= lo:
+                    assert cnt == 0
+                    continue
+                assert anim == (1 if lo == 0 else 2) and first == lo - (anim == 2) and cnt == hi - lo + (anim == 2)
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))

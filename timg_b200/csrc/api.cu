@@ -385,7 +385,7 @@ int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const 
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
     B2_TRY(batch_scale(ctx, b, d_src, d_fb, b->out_h, &cs));
     if (ctx->ev_after_scale) B2_CUDA(ctx, cudaEventRecord(ctx->ev_after_scale, ctx->stream));
-    return launch_blocks(ctx, d_fb, nullptr, b->animation ? 2 : 0, b->out_w, b->out_h, b->n_frames, b->flags,
+    return launch_blocks(ctx, d_fb, nullptr, b->animation == 2 ? 3 : b->animation ? 2 : 0, b->out_w, b->out_h, b->n_frames, b->flags,
                          b->x_indent_cells, d_out, out_cap, d_offsets);
 }
 
@@ -463,18 +463,21 @@ static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uin
     const size_t frame_bytes = src_frame_bytes(b);
     int chunk = (int)std::max<size_t>(1, ((size_t)672 << 20) / frame_bytes);
     if (const char *e = getenv("B200TIMG_CHUNK_FRAMES")) chunk = std::max(1, atoi(e));      // test knob
-    if (!sixel && b->animation) chunk = b->n_frames;          // delta frames chain through the whole batch
+    // delta-encoded animations chain frame to frame: every chunk after the first re-uploads its predecessor's last
+    // frame as a halo (animation = 2: scaled, used as the reference of the chunk's first frame, not emitted)
+    const bool anim = !sixel && b->animation != 0;
     chunk = std::min(chunk, b->n_frames);
     const int n_chunks = (b->n_frames + chunk - 1) / chunk;
     const size_t blocks_bound = sixel ? b200timg_sixel_bound(b->out_w, round_to_sixel(b->out_h)) * (size_t)chunk
                                       : b200timg_blocks_bound(b->out_w, b->out_h) * (size_t)chunk + 64;
-    for (int i = 0; i < 2 && i < n_chunks; ++i) B2_CUDA(ctx, ctx->pipe_in[i].reserve(frame_bytes * chunk));
-    B2_CUDA(ctx, ctx->offsets.reserve((size_t)(chunk + 1) * sizeof(uint64_t)));
-    B2_CUDA(ctx, ctx->pinned.reserve((size_t)(chunk + 1) * sizeof(uint64_t)));
+    for (int i = 0; i < 2 && i < n_chunks; ++i) B2_CUDA(ctx, ctx->pipe_in[i].reserve(frame_bytes * (chunk + 1)));
+    B2_CUDA(ctx, ctx->offsets.reserve((size_t)(chunk + 2) * sizeof(uint64_t)));
+    B2_CUDA(ctx, ctx->pinned.reserve((size_t)(chunk + 2) * sizeof(uint64_t)));
     uint64_t *h_offs = ctx->pinned.as<uint64_t>();
 
     auto upload_chunk = [&](int k) -> int {
-        const int i = k & 1, f0 = k * chunk, nf = std::min(chunk, b->n_frames - f0);
+        const int i = k & 1, halo = (anim && k > 0) ? 1 : 0;
+        const int f0 = k * chunk - halo, nf = std::min(chunk, b->n_frames - k * chunk) + halo;
         B2_CUDA(ctx, cudaMemcpyAsync(ctx->pipe_in[i].p, src + (size_t)f0 * frame_bytes, frame_bytes * nf,
                                      cudaMemcpyHostToDevice, ctx->copy_stream));
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_up[i], ctx->copy_stream));
@@ -486,8 +489,10 @@ static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uin
     offsets[0] = 0;
     for (int k = 0; k < n_chunks; ++k) {
         const int i = k & 1, f0 = k * chunk, nf = std::min(chunk, b->n_frames - f0);
+        const int halo = (anim && k > 0) ? 1 : 0;             // the sub-batch then starts one frame early
         b200timg_batch sub = *b;
-        sub.n_frames = nf;
+        sub.n_frames = nf + halo;
+        if (halo) sub.animation = 2;
         const uint8_t *d_in = ctx->pipe_in[i].as<uint8_t>();
         B2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[i], 0));
         if (k >= 2) B2_CUDA(ctx, cudaEventSynchronize(ctx->ev_d2h[i]));            // pipe_out[i] is free again
@@ -502,11 +507,11 @@ static int batch_host_impl(b200timg_ctx *ctx, const b200timg_batch *b, const uin
             B2_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scaled[i], 0));
             B2_TRY(upload_chunk(k + 2));
         }
-        B2_CUDA(ctx, cudaMemcpyAsync(h_offs, ctx->offsets.p, (size_t)(nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        B2_CUDA(ctx, cudaMemcpyAsync(h_offs, ctx->offsets.p, (size_t)(nf + halo + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(ctx, cudaEventRecord(ctx->ev_prep, ctx->stream));
         B2_CUDA(ctx, cudaEventSynchronize(ctx->ev_prep));                          // sizes of this chunk are on the host
-        const size_t total = (size_t)h_offs[nf];
-        for (int j = 1; j <= nf; ++j) offsets[f0 + j] = base_bytes + h_offs[j];
+        const size_t total = (size_t)h_offs[nf + halo];                            // a halo frame contributes no bytes
+        for (int j = 1; j <= nf; ++j) offsets[f0 + j] = base_bytes + h_offs[j + halo];
         if (base_bytes + total > out_cap) {
             return ctx->fail(B200TIMG_ENOSPC, "batch: need more than %zu bytes (have %zu)", base_bytes + total, out_cap);
         }

@@ -175,7 +175,7 @@ struct BlocksParams {
     int w, h, n_frames, cols, rows;       // cols = cells per row, rows = row pairs
     int quarter, upper, color8, indent;
     int row_offset;                       // -1 when odd height and lower block (:356-358)
-    int prev_mode;                        // 0 none, 1 explicit prev, 2 animation
+    int prev_mode;                        // 0 none, 1 explicit prev, 2 animation, 3 animation whose frame 0 is a halo (not emitted)
     long long frame_px;
 };
 
@@ -194,7 +194,7 @@ blocks_pick_kernel(const uint32_t *__restrict__ fb, const uint32_t *__restrict__
     const uint32_t *frame = fb + (long long)f * P.frame_px;
     const uint32_t *prev = nullptr;
     if (P.prev_mode == 1) prev = prev_single;
-    else if (P.prev_mode == 2 && f > 0) prev = fb + (long long)(f - 1) * P.frame_px;
+    else if (P.prev_mode >= 2 && f > 0) prev = fb + (long long)(f - 1) * P.frame_px;
 
     const int top_row = 2 * r + P.row_offset, bot_row = top_row + 1;
     const bool top_ok = top_row >= 0, bot_ok = bot_row < P.h;
@@ -338,6 +338,7 @@ blocks_rowscan_kernel(BlocksParams P, RowRec *__restrict__ rows, FrameRec *__res
             fr.trailing = (uint32_t)(P.rows - 1 - c_last);
             fr.size = c_run + (fr.trailing ? 3 + ndig(fr.trailing) : 0);  // :397-399
         }
+        if (P.prev_mode == 3 && f == 0) { fr.size = 0; fr.trailing = 0; }   // halo frame of a sharded animation: reference only
         frames[f] = fr;
     }
 }
@@ -399,7 +400,7 @@ blocks_emit_kernel(BlocksParams P, const CellRec *__restrict__ cells, const RowR
     const RowRec rr = rows[(long long)f * P.rows + r];
     const FrameRec fr = frames[f];
     const unsigned long long fbase = offsets[f];
-    if (fbase + fr.size > out_cap) return;                 // never write out of bounds
+    if (fr.size == 0 || fbase + fr.size > out_cap) return; // nothing to write / never write out of bounds
     if (r == 0 && tid == 0 && fr.size && fr.trailing) {    // trailing cursor-down, :397-399
         char *o = out + fbase + fr.size - (3 + ndig(fr.trailing));
         *o++ = '\033'; *o++ = '['; o = put_num(o, fr.trailing); *o++ = 'B';

@@ -18,6 +18,17 @@ def shard_range(n_frames, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def animation_chunk(n_frames, rank, world):
+    """Delta-encoded animations (block modes): frame k depends on frame k-1's SCALED PIXELS only (the backing
+    store equals the previous frame, src/unicode-block-canvas.cc:244,310), so a rank that owns [lo, hi) loads one
+    extra halo frame lo-1 and encodes with Batch.animation = 2 (frame 0 of the batch is then a reference only).
+    Returns (first frame to load, frames to load, animation flag)."""
+    lo, hi = shard_range(n_frames, rank, world)
+    if hi <= lo:
+        return lo, 0, 1
+    return (lo, hi - lo, 1) if lo == 0 else (lo - 1, hi - lo + 1, 2)
+
+
 class _Gather:
     """An in-flight gather_encoded_async: wait() finishes it (on NCCL that makes the *current CUDA
     stream* wait, not the host) and returns what gather_encoded returns."""
