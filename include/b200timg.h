@@ -120,6 +120,11 @@ int b200timg_yuv_scale(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int
 int b200timg_compose_bg(b200timg_ctx *ctx, uint8_t *fb, int w, int h, int has_bg,
                         uint32_t bg, uint32_t pattern, int pattern_w, int pattern_h,
                         int start_row);
+/* b200timg_compose_bg on the copy b200timg_has_transparency(fb, w, h) just uploaded (one upload for "scan, fetch the
+ * background colour lazily, compose"); falls back to b200timg_compose_bg if that copy is gone. */
+int b200timg_compose_bg_resident(b200timg_ctx *ctx, uint8_t *fb, int w, int h, int has_bg,
+                                 uint32_t bg, uint32_t pattern, int pattern_w, int pattern_h,
+                                 int start_row);
 /* *result = 1 if any pixel at or after start_row has alpha < 255 (the reference's
  * early-out scan, src/framebuffer.cc:113-117). */
 int b200timg_has_transparency(b200timg_ctx *ctx, const uint8_t *fb, int w, int h,

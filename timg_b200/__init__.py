@@ -51,6 +51,8 @@ ABI = {
     "b200timg_yuv_scale": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]),
     "b200timg_compose_bg": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
                                       C.c_int, C.c_int, C.c_int]),
+    "b200timg_compose_bg_resident": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                               C.c_int, C.c_int, C.c_int]),
     "b200timg_has_transparency": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "b200timg_blocks_bound": (C.c_size_t, [C.c_int, C.c_int]),
     "b200timg_blocks_encode": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int,

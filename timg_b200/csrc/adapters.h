@@ -94,7 +94,7 @@ inline std::unique_ptr<ImageScaler> B200CreateImageScaler(int, int, ImageScaler:
 // called when the frame really has a pixel with alpha < 255 at or after start_row.
 inline void B200AlphaComposeBackground(Framebuffer *fb, const Framebuffer::bgcolor_query &get_bg,
                                        rgba_t pattern, int pwidth, int pheight, int start_row = 0) {
-    if (!get_bg) return;
+    if (!get_bg || start_row >= fb->height()) return;
     std::lock_guard<std::mutex> l(B200Context::Lock());
     int transparent = 0;
     B200Context::Check(b200timg_has_transparency(B200Context::Get(), (const uint8_t *)fb->begin(), fb->width(),
@@ -102,8 +102,9 @@ inline void B200AlphaComposeBackground(Framebuffer *fb, const Framebuffer::bgcol
                        "has_transparency");
     if (!transparent) return;
     const rgba_t bg = get_bg();
-    B200Context::Check(b200timg_compose_bg(B200Context::Get(), (uint8_t *)fb->begin(), fb->width(), fb->height(), 1,
-                                           B200PackColor(bg), B200PackColor(pattern), pwidth, pheight, start_row),
+    // the frame is still on the device from the transparency test: compose that copy, one upload in total
+    B200Context::Check(b200timg_compose_bg_resident(B200Context::Get(), (uint8_t *)fb->begin(), fb->width(), fb->height(), 1,
+                                                    B200PackColor(bg), B200PackColor(pattern), pwidth, pheight, start_row),
                        "compose");
 }
 
@@ -173,23 +174,30 @@ public:
         MoveCursorDX(x / options_.cell_x_px);
         const int w = fb_orig.width(), hp = RoundToSixel(fb_orig.height());
         Framebuffer fb(w, hp);                                                          // .cc:111-120
-        B200AlphaComposeBackground(&fb, options_.bgcolor_getter, options_.bg_pattern_color,
-                                   options_.pattern_size * options_.cell_x_px,
-                                   options_.pattern_size * options_.cell_y_px / 2, fb_orig.height());
+        // the pad strip (<= 5 rows) is composed by the reference's own member function, exactly as the reference does
+        fb.AlphaComposeBackground(options_.bgcolor_getter, options_.bg_pattern_color,
+                                  options_.pattern_size * options_.cell_x_px,
+                                  options_.pattern_size * options_.cell_y_px / 2, fb_orig.height());
         std::copy(fb_orig.begin(), fb_orig.end(), fb.begin());
-        // The stream is sized exactly by the library before it is written, so no worst-case guess
-        // like the reference's 1024 + w*h*5 (.cc:123) is needed: ask, allocate, encode.
-        size_t need = 0;
-        std::lock_guard<std::mutex> l(B200Context::Lock());
-        int rc = b200timg_sixel_encode(B200Context::Get(), (const uint8_t *)fb.begin(), w, hp, nullptr, 0, &need);
-        if (rc != B200TIMG_ENOSPC) B200Context::Check(rc, "sixel size");
+        // One encode pass.  Start with the reference's own guess (.cc:123); the library reports the exact size
+        // needed (and writes nothing) should a frame ever exceed it.
+        size_t cap = 1024 + (size_t)w * hp * 5, n = 0;
         const size_t extra = 1024;
-        char *buffer = new char[need + extra];
+        char *buffer = new char[cap + extra];
         char *pos = AppendPrefixToBuffer(buffer);
+        const size_t prefix_len = (size_t)(pos - buffer);
         pos = (char *)memcpy(pos, before_, strlen(before_)) + strlen(before_);          // .cc:133
-        size_t n = 0;
-        B200Context::Check(b200timg_sixel_encode(B200Context::Get(), (const uint8_t *)fb.begin(), w, hp, pos, need, &n),
-                           "sixel_encode");
+        std::lock_guard<std::mutex> l(B200Context::Lock());
+        int rc = b200timg_sixel_encode(B200Context::Get(), (const uint8_t *)fb.begin(), w, hp, pos, cap - prefix_len, &n);
+        if (rc == B200TIMG_ENOSPC) {
+            char *bigger = new char[n + prefix_len + extra];
+            memcpy(bigger, buffer, (size_t)(pos - buffer));
+            pos = bigger + (pos - buffer);
+            delete[] buffer;
+            buffer = bigger;
+            rc = b200timg_sixel_encode(B200Context::Get(), (const uint8_t *)fb.begin(), w, hp, pos, n, &n);
+        }
+        B200Context::Check(rc, "sixel_encode");
         pos += n;
         pos = (char *)memcpy(pos, after_, strlen(after_)) + strlen(after_);             // .cc:150
         write_sequencer_->WriteBuffer(OutBuffer(buffer, (size_t)(pos - buffer)), seq_type, end_of_frame);

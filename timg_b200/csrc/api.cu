@@ -71,7 +71,7 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     ctx->gather_status.release();
     ctx->in_stage.release(); ctx->fb_scaled.release(); ctx->prev_stage.release();
     ctx->out_stage.release(); ctx->offsets.release(); ctx->cells.release(); ctx->rows.release();
-    ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release(); ctx->scale_list.release(); ctx->tri_tables.release();
+    ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release(); ctx->scale_list.release(); ctx->scale_tmp.release(); ctx->tri_tables.release();
     ctx->pinned.release(); ctx->pinned_io.release();
     for (int i = 0; i < 2; ++i) { ctx->pipe_in[i].release(); ctx->pipe_out[i].release(); }
     if (ctx->pipe_ready) {
@@ -208,10 +208,26 @@ int b200timg_compose_bg(b200timg_ctx *ctx, uint8_t *fb, int w, int h, int has_bg
     B2_TRY(check_ctx(ctx));
     if (!fb || w <= 0 || h <= 0) return ctx->fail(B200TIMG_EINVAL, "compose: bad args");
     const size_t bytes = (size_t)w * h * 4;
+    ctx->resident_fb = nullptr;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
     B2_TRY(upload(ctx, ctx->fb_scaled.p, fb, bytes));
     B2_TRY(launch_compose(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, has_bg, bg, pattern, pw, ph, start_row));
     B2_TRY(download(ctx, fb, ctx->fb_scaled.p, bytes));
+    return sync(ctx);
+}
+
+// Compose the frame b200timg_has_transparency uploaded last (same fb, w, h) and download the result: the adapter's
+// "scan, ask for the background colour only if needed, compose" costs one upload instead of two.
+int b200timg_compose_bg_resident(b200timg_ctx *ctx, uint8_t *fb, int w, int h, int has_bg, uint32_t bg,
+                                 uint32_t pattern, int pw, int ph, int start_row) {
+    B2_TRY(check_ctx(ctx));
+    if (!fb || w <= 0 || h <= 0) return ctx->fail(B200TIMG_EINVAL, "compose: bad args");
+    if (ctx->resident_fb != fb || ctx->resident_w != w || ctx->resident_h != h)
+        return b200timg_compose_bg(ctx, fb, w, h, has_bg, bg, pattern, pw, ph, start_row);     // nothing resident: plain path
+    const size_t bytes = (size_t)w * h * 4;
+    B2_TRY(launch_compose(ctx, ctx->fb_scaled.as<uint8_t>(), w, h, 1, has_bg, bg, pattern, pw, ph, start_row));
+    B2_TRY(download(ctx, fb, ctx->fb_scaled.p, bytes));
+    ctx->resident_fb = nullptr;
     return sync(ctx);
 }
 
@@ -229,6 +245,7 @@ int b200timg_has_transparency(b200timg_ctx *ctx, const uint8_t *fb, int w, int h
     B2_TRY(download(ctx, ctx->pinned.p, ctx->misc.p, sizeof(int)));
     B2_TRY(sync(ctx));
     *result = *ctx->pinned.as<int>() ? 1 : 0;
+    ctx->resident_fb = fb; ctx->resident_w = w; ctx->resident_h = h;      // still in ctx->fb_scaled for b200timg_compose_bg_resident
     return B200TIMG_OK;
 }
 
@@ -245,6 +262,7 @@ int b200timg_blocks_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, c
     if (!fb || !size || w <= 0 || h <= 0 || (!out && cap)) return ctx->fail(B200TIMG_EINVAL, "blocks: bad args");
     const size_t bytes = (size_t)w * h * 4;
     const size_t bound = b200timg_blocks_bound(w, h) + 32;
+    ctx->resident_fb = nullptr;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
     B2_CUDA(ctx, ctx->out_stage.reserve(bound));
     B2_CUDA(ctx, ctx->offsets.reserve(2 * sizeof(uint64_t)));
@@ -286,6 +304,7 @@ int b200timg_scale_rgba_mode(b200timg_ctx *ctx, const uint8_t *in, int iw, int i
     if (!in || !out || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return ctx->fail(B200TIMG_EINVAL, "scale: bad args");
     const size_t ib = (size_t)iw * ih * 4, ob = (size_t)ow * oh * 4;
     B2_CUDA(ctx, ctx->in_stage.reserve(ib));
+    ctx->resident_fb = nullptr;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(ob));
     B2_TRY(upload(ctx, ctx->in_stage.p, in, ib));
     if (fast == 2) B2_TRY(launch_scale_bilinear(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1, nullptr));
@@ -301,6 +320,7 @@ int b200timg_yuv_scale(b200timg_ctx *ctx, const uint8_t *in, int iw, int ih, int
         return ctx->fail(B200TIMG_EINVAL, "yuv_scale: bad args");
     const size_t ib = (size_t)iw * ih + 2 * (size_t)(iw / 2) * (ih / 2), ob = (size_t)ow * oh * 4;
     B2_CUDA(ctx, ctx->in_stage.reserve(ib));
+    ctx->resident_fb = nullptr;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(ob));
     B2_TRY(upload(ctx, ctx->in_stage.p, in, ib));
     B2_TRY(launch_yuv_scale(ctx, ctx->in_stage.as<uint8_t>(), iw, ih, fmt, ctx->fb_scaled.as<uint8_t>(), ow, oh, oh, 1));
@@ -325,6 +345,7 @@ int b200timg_sixel_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, ch
     // one pass: the frame is encoded into a device staging buffer of worst-case size, and exactly the
     // encoded bytes come back (or ENOSPC with the size needed, nothing copied)
     const size_t bytes = (size_t)w * h * 4, bound = b200timg_sixel_bound(w, h);
+    ctx->resident_fb = nullptr;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(bytes));
     B2_CUDA(ctx, ctx->out_stage.reserve(bound));
     B2_CUDA(ctx, ctx->offsets.reserve(2 * sizeof(uint64_t)));
@@ -380,6 +401,7 @@ int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const 
     B2_TRY(validate_batch(ctx, b));
     if (!d_src || !d_out || !d_offsets) return ctx->fail(B200TIMG_EINVAL, "batch: null pointer");
     const size_t fb_bytes = (size_t)b->out_w * b->out_h * 4 * b->n_frames;
+    ctx->resident_fb = nullptr;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(fb_bytes));
     uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
@@ -399,6 +421,7 @@ static int sixel_batch_phases(b200timg_ctx *ctx, const b200timg_batch *b, const 
     // transparent pixels, compose the background into the pad strip only, keep the rest.
     const int hp = round_to_sixel(b->out_h);
     const size_t frame_bytes = (size_t)b->out_w * hp * 4;
+    ctx->resident_fb = nullptr;
     B2_CUDA(ctx, ctx->fb_scaled.reserve(frame_bytes * b->n_frames));
     uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
     // scale with AlphaComposeBackground fused into the epilogue (what the sources do, e.g.

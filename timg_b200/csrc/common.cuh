@@ -57,6 +57,8 @@ struct b200timg_ctx {
     int plan_key[4] = {0, 0, 0, 0};           // ... for this iw, ih, ow, oh (device copy in `tables`)
     long long fixed_geom_key = -1;            // which tile-origin arrays are uploaded behind ctx->misc + 4096
     size_t sixel_idx_off = 0;                 // where the last sixel encode put its index planes
+    const void *resident_fb = nullptr;        // host frame whose copy b200timg_has_transparency left in fb_scaled ...
+    int resident_w = 0, resident_h = 0;       // ... (cleared by anything else that writes fb_scaled)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
@@ -82,6 +84,7 @@ struct b200timg_ctx {
     b200timg::DevBuf tri_tables;   // bilinear / YUV scaler tap tables ...
     int tri_key[5] = {0, 0, 0, 0, 0};          // ... for this (kind, iw, ih, ow, oh), device pointers cached in tri_params
     std::vector<char> tri_params;
+    b200timg::DevBuf scale_tmp;    // float4 intermediate + flags of the two-pass scaler (long filters)
     b200timg::DevBuf scale_list;   // work list of tiles the opaque-only scaler hands to the general one
     b200timg::HostBuf pinned;      // staging for sizes / offsets
     b200timg::HostBuf pinned_io;   // staging for pageable payloads

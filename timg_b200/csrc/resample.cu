@@ -794,6 +794,111 @@ static TiledFn pick_h(int hclass, int vclass) {
 }
 static int tap_class(int widest) { return widest <= 4 ? 4 : widest <= 6 ? 6 : widest <= 8 ? 8 : 0; }
 
+
+// ---- two-pass kernels for long filters (> 8 taps on an axis: strong downscales such as 4K -> a grid cell,
+// 1080p -> 160 columns) -----------------------------------------------------------------------------
+// The tiled kernel above stages a whole 2-D window per tile; with 24..48 taps per axis the window no longer
+// fits and its halo dwarfs the tile.  Here each pass is a plain 1-D filter over a float4 intermediate image
+// (R*A, G*A, B*A, A) kept in global memory (a few MB per frame, written and read once):
+//   pass 1 (the axis the reference's cost model runs first) decodes the source bytes on the fly,
+//   pass 2 filters the intermediate, un-weights, encodes, composes.
+// Same arithmetic and summation order as resample_direct_kernel (vertical taps in row order; horizontal taps
+// alternating between two accumulators, or sequential when <= 3).  Output pixels whose filtered alpha is below
+// 2^-120 need the un-weighted colour planes: pass 2 raises a per-frame flag for them and a second pair of
+// passes (which return at once when the flag is down -- always, for opaque sources) fills them in.
+struct TwoPassParams {
+    ResampleParams P;
+    float4 *tmp;                 // [n_frames][first-pass rows][first-pass cols]
+    int *need_plain;             // [n_frames] raised by the weighted second pass
+    unsigned char *mask;         // [n_frames][oh][ow] 1 = this pixel's filtered alpha is < 2^-120
+};
+
+template <bool PLAIN> __device__ __forceinline__ float4 decode_tp(uint32_t p, int bgra) { return PLAIN ? decode_plain(p, bgra) : decode_pm(p, bgra); }
+
+// pass 1, vertical first: tmp[oy][x] = sum_k decode(src[vfirst[oy] + k][x]) * vc[oy][k]
+template <bool PLAIN>
+__global__ void __launch_bounds__(256)
+twopass_v1_kernel(const uint32_t *__restrict__ in, TwoPassParams T) {
+    const ResampleParams &P = T.P;
+    const int x = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y, f = blockIdx.z;
+    if (PLAIN && !T.need_plain[f]) return;
+    if (x >= P.iw) return;
+    const uint32_t *src = in + (long long)f * P.iw * P.ih + (long long)P.v_first[oy] * P.iw + x;
+    const float *vc = P.v_coeff + (long long)oy * P.v_widest;
+    const int cnt = P.v_count[oy];
+    float4 a = mul4(decode_tp<PLAIN>(src[0], P.bgra), vc[0]);
+    for (int k = 1; k < cnt; ++k) a = add4(a, mul4(decode_tp<PLAIN>(src[(long long)k * P.iw], P.bgra), vc[k]));
+    T.tmp[((long long)f * P.oh + oy) * P.iw + x] = a;
+}
+// pass 1, horizontal first: tmp[y][ox] = sum_i decode(src[y][hfirst[ox] + i]) * hc[ox][i]
+template <bool PLAIN>
+__global__ void __launch_bounds__(256)
+twopass_h1_kernel(const uint32_t *__restrict__ in, TwoPassParams T) {
+    const ResampleParams &P = T.P;
+    const int ox = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), f = blockIdx.z;
+    if (PLAIN && !T.need_plain[f]) return;
+    if (ox >= P.ow || y >= P.ih) return;
+    const uint32_t *row = in + (long long)f * P.iw * P.ih + (long long)y * P.iw + P.h_first[ox];
+    const float *hc = P.h_coeff + (long long)ox * P.h_widest;
+    const int cnt = P.h_count[ox];
+    float4 r;
+    if (P.h_sequential) {
+        r = mul4(decode_tp<PLAIN>(row[0], P.bgra), hc[0]);
+        for (int i = 1; i < cnt; ++i) r = add4(r, mul4(decode_tp<PLAIN>(row[i], P.bgra), hc[i]));
+    } else {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a0 = z, a1 = z;
+        for (int i = 0; i < cnt; ++i) { const float4 t = mul4(decode_tp<PLAIN>(row[i], P.bgra), hc[i]); if (i & 1) a1 = add4(a1, t); else a0 = add4(a0, t); }
+        r = add4(a0, a1);
+    }
+    T.tmp[((long long)f * P.ih + y) * P.ow + ox] = r;
+}
+// pass 2: filter the intermediate along the other axis, then un-weight / encode / compose (weighted pass) or
+// fill in the pixels whose alpha came out as zero (plain pass)
+template <bool VFIRST, bool PLAIN>
+__global__ void __launch_bounds__(256)
+twopass_2_kernel(uint32_t *__restrict__ out, TwoPassParams T) {
+    const ResampleParams &P = T.P;
+    const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5), f = blockIdx.z;
+    if (PLAIN && !T.need_plain[f]) return;
+    if (ox >= P.ow || oy >= P.oh) return;
+    const float tiny = 7.5231638452626401e-37f;       // 2^-120
+    uint32_t *dst = out + ((long long)f * P.out_frame_rows + oy) * P.ow + ox;
+    float4 r;
+    if (VFIRST) {                                     // second pass is horizontal, over tmp[oy][0..iw)
+        const float4 *row = T.tmp + ((long long)f * P.oh + oy) * P.iw + P.h_first[ox];
+        const float *hc = P.h_coeff + (long long)ox * P.h_widest;
+        const int cnt = P.h_count[ox];
+        if (P.h_sequential) {
+            r = mul4(row[0], hc[0]);
+            for (int i = 1; i < cnt; ++i) r = add4(r, mul4(row[i], hc[i]));
+        } else {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 a0 = z, a1 = z;
+            for (int i = 0; i < cnt; ++i) { const float4 t = mul4(row[i], hc[i]); if (i & 1) a1 = add4(a1, t); else a0 = add4(a0, t); }
+            r = add4(a0, a1);
+        }
+    } else {                                          // second pass is vertical, over tmp[0..ih)[ox]
+        const float4 *col = T.tmp + ((long long)f * P.ih + P.v_first[oy]) * P.ow + ox;
+        const float *vc = P.v_coeff + (long long)oy * P.v_widest;
+        const int cnt = P.v_count[oy];
+        r = mul4(col[0], vc[0]);
+        for (int k = 1; k < cnt; ++k) r = add4(r, mul4(col[(long long)k * P.ow], vc[k]));
+    }
+    float v[7];
+    unsigned char *m = T.mask + ((long long)f * P.oh + oy) * P.ow + ox;
+    if (!PLAIN) {
+        const bool hole = r.w < tiny;                 // un-weighted colour needed: left to the plain passes
+        *m = hole ? 1 : 0;
+        if (hole) { T.need_plain[f] = 1; return; }    // (every writer stores 1: benign)
+        v[0] = v[1] = v[2] = 0.f; v[3] = r.w; v[4] = r.x; v[5] = r.y; v[6] = r.z;
+        *dst = compose_at(P.cs, encode_px(v), ox, oy);
+    } else if (*m) {
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = 0.f; v[4] = v[5] = v[6] = 0.f;   // alpha < 2^-120 encodes to 0 either way
+        *dst = compose_at(P.cs, encode_px(v), ox, oy);
+    }
+}
+
 // both axes point-sampled (scale 1): plain copy, with the BGRA swizzle if asked (:6938-6940).
 __global__ void __launch_bounds__(256)
 resample_copy_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P) {
@@ -859,10 +964,10 @@ template <bool EXACT> __device__ __forceinline__ float byte_val(uint32_t p, uint
 }
 
 struct V3Geom { int nix, niy, sp, tp; unsigned grp_magic; const int32_t *tile_ix0, *tile_iy0; uint32_t *fallback; };   // grp_magic: floor(2^32/(sp/4))+1
-constexpr int V3_TW = 64, V3_TH = 32, V3_NT = 256;
+constexpr int V3_TW = 64, V3_TH = 32, V3_NT = 256, V3_MINB = 2;
 
 template <int HC, int VC, bool EXACT>
-__global__ void __launch_bounds__(V3_NT, 3)
+__global__ void __launch_bounds__(V3_NT, V3_MINB)
 resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, V3Geom G) {
     extern __shared__ float4 s_px[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.z;
@@ -1243,6 +1348,39 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
                 B2_LAUNCH_CHECK(ctx);
                 return B200TIMG_OK;
             }
+        }
+        if (!getenv("B200TIMG_NO_TWOPASS")) {
+            // long filters: two 1-D passes over a float4 intermediate in global memory
+            const size_t t_elems = pl->vertical_first ? (size_t)oh * iw : (size_t)ih * ow;
+            const size_t o_tmp = 0, o_flag = (sizeof(float4) * t_elems * n_frames + 255) / 256 * 256;
+            const size_t o_mask = o_flag + (sizeof(int) * (size_t)n_frames + 255) / 256 * 256;
+            B2_CUDA(ctx, ctx->scale_tmp.reserve(o_mask + (size_t)ow * oh * n_frames));
+            char *tb = ctx->scale_tmp.as<char>();
+            TwoPassParams T;
+            T.P = P; T.tmp = reinterpret_cast<float4 *>(tb + o_tmp); T.need_plain = reinterpret_cast<int *>(tb + o_flag);
+            T.mask = reinterpret_cast<unsigned char *>(tb + o_mask);
+            B2_CUDA(ctx, cudaMemsetAsync(T.need_plain, 0, sizeof(int) * (size_t)n_frames, ctx->stream));
+            const dim3 g2((ow + 31) / 32, (oh + 7) / 8, n_frames);
+            for (int plain = 0; plain < 2; ++plain) {
+                if (pl->vertical_first) {
+                    const dim3 g1((iw + 255) / 256, oh, n_frames);
+                    B2_KERNEL(ctx, plain ? "twopass_plain_kernels" : "twopass_v1_kernel");
+                    if (plain) twopass_v1_kernel<true><<<g1, 256, 0, ctx->stream>>>(in, T); else twopass_v1_kernel<false><<<g1, 256, 0, ctx->stream>>>(in, T);
+                    B2_LAUNCH_CHECK(ctx);
+                    B2_KERNEL(ctx, plain ? "twopass_plain_kernels" : "twopass_2_kernel");
+                    if (plain) twopass_2_kernel<true, true><<<g2, 256, 0, ctx->stream>>>(out, T); else twopass_2_kernel<true, false><<<g2, 256, 0, ctx->stream>>>(out, T);
+                    B2_LAUNCH_CHECK(ctx);
+                } else {
+                    const dim3 g1((ow + 31) / 32, (ih + 7) / 8, n_frames);
+                    B2_KERNEL(ctx, plain ? "twopass_plain_kernels" : "twopass_h1_kernel");
+                    if (plain) twopass_h1_kernel<true><<<g1, 256, 0, ctx->stream>>>(in, T); else twopass_h1_kernel<false><<<g1, 256, 0, ctx->stream>>>(in, T);
+                    B2_LAUNCH_CHECK(ctx);
+                    B2_KERNEL(ctx, plain ? "twopass_plain_kernels" : "twopass_2_kernel");
+                    if (plain) twopass_2_kernel<false, true><<<g2, 256, 0, ctx->stream>>>(out, T); else twopass_2_kernel<false, false><<<g2, 256, 0, ctx->stream>>>(out, T);
+                    B2_LAUNCH_CHECK(ctx);
+                }
+            }
+            return B200TIMG_OK;
         }
         // tile shape: largest of a few candidates whose decoded window + intermediate fit in shared memory
         static const int cand[][2] = {{64, 16}, {32, 16}, {32, 8}, {16, 8}, {8, 4}};
