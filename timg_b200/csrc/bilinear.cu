@@ -104,6 +104,98 @@ yuv420_rgba_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, Y
     out[((long long)f * P.out_frame_rows + oy) * P.ow + ox] = pack_rgba(sat8(r), sat8(g), sat8(b), 0xffu);
 }
 
+
+// ---- tiled variant: the same filter, separable inside a 64 x 32 output tile -------------------------
+// The per-pixel kernel above redoes the horizontal taps of every source row for every output row that uses
+// it.  Here a tile stages its luma / chroma byte windows in shared memory once, runs the vertical taps into
+// float rows (luma at source width, chroma at half the OUTPUT width after its own horizontal pass order is
+// swapped: vertical first for both), then the horizontal taps, converts and stores.  Needs iw % 8 == 0.
+constexpr int YT_W = 64, YT_H = 32, YT_NT = 256;
+struct YuvTileGeom { int nix, niy, ncx, ncy; };        // window extents (luma cols/rows, chroma cols/rows), maxima over tiles
+
+__global__ void __launch_bounds__(YT_NT)
+yuv420_rgba_tiled_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, YuvParams P, YuvTileGeom G) {
+    extern __shared__ __align__(16) uint8_t s_yuv[];
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int ox0 = blockIdx.x * YT_W, oy0 = blockIdx.y * YT_H;
+    const int tw = min(YT_W, P.ow - ox0), th = min(YT_H, P.oh - oy0);
+    const int cxa = ox0 >> 1, ncol = (tw + 1) >> 1;               // output chroma columns of this tile: [cxa, cxa + ncol)
+    const int cw = P.iw >> 1, chh = P.ih >> 1;
+    // window origins (tables are monotone), luma x origin aligned down to 4 bytes, chroma x origin to 4 samples
+    const int ix0 = P.yh.first[ox0] & ~3, iy0 = P.yv.first[oy0];
+    const int cx0 = P.ch.first[cxa] & ~3, cy0 = P.cv.first[oy0];
+    const int nixw = (G.nix + 7) >> 2, ncxw = (G.ncx + 7) >> 2;   // words per staged row (origin alignment slack included)
+    const int ypitch = nixw * 4, cpitch = ncxw * 4;
+    uint8_t *Yw = s_yuv;                                     // [niy][ypitch]
+    uint8_t *Uw = Yw + G.niy * ypitch, *Vw = Uw + G.ncy * cpitch;   // [ncy][cpitch] each
+    float *TY = reinterpret_cast<float *>(Vw + G.ncy * cpitch + ((16 - ((G.niy * ypitch + 2 * G.ncy * cpitch) & 15)) & 15));   // [YT_H][ypitch]
+    float *TU = TY + YT_H * ypitch, *TV = TU + YT_H * cpitch;    // [YT_H][cpitch]
+    const uint8_t *Y = in + (long long)f * P.frame_bytes;
+    const uint8_t *C = Y + (long long)P.iw * P.ih;
+    for (int u = tid; u < G.niy * nixw; u += YT_NT) {
+        const int ly = u / nixw, g = u - ly * nixw, y = iy0 + ly, x = ix0 + 4 * g;
+        uint32_t v = 0;
+        if (y < P.ih && x < P.iw) v = __ldg(reinterpret_cast<const uint32_t *>(Y + (long long)y * P.iw + x));
+        reinterpret_cast<uint32_t *>(Yw + ly * ypitch)[g] = v;
+    }
+    for (int u = tid; u < G.ncy * ncxw; u += YT_NT) {
+        const int ly = u / ncxw, g = u - ly * ncxw, y = cy0 + ly, x = cx0 + 4 * g;
+        uint32_t pu = 0, pv = 0;
+        if (y < chh && x < cw) {
+            if (P.nv12) {
+                const uint2 q = __ldg(reinterpret_cast<const uint2 *>(C + ((long long)y * cw + x) * 2));      // U0 V0 U1 V1 | U2 V2 U3 V3
+                pu = __byte_perm(q.x, q.y, 0x6420); pv = __byte_perm(q.x, q.y, 0x7531);
+            } else {
+                pu = __ldg(reinterpret_cast<const uint32_t *>(C + (long long)y * cw + x));
+                pv = __ldg(reinterpret_cast<const uint32_t *>(C + (long long)cw * chh + (long long)y * cw + x));
+            }
+        }
+        reinterpret_cast<uint32_t *>(Uw + ly * cpitch)[g] = pu;
+        reinterpret_cast<uint32_t *>(Vw + ly * cpitch)[g] = pv;
+    }
+    __syncthreads();
+    // vertical taps: luma rows -> TY, chroma rows -> TU / TV
+    for (int u = tid; u < th * ypitch; u += YT_NT) {
+        const int ty = u / ypitch, x = u - ty * ypitch, oy = oy0 + ty;
+        const int y0 = P.yv.first[oy] - iy0, ny = P.yv.count[oy];
+        const float *hy = P.yv.coeff + (long long)oy * P.yv.widest;
+        float a = 0.0f;
+        for (int j = 0; j < ny; ++j) a = fmaf((float)Yw[(y0 + j) * ypitch + x], hy[j], a);
+        TY[ty * ypitch + x] = a;
+    }
+    for (int u = tid; u < th * cpitch; u += YT_NT) {
+        const int ty = u / cpitch, x = u - ty * cpitch, oy = oy0 + ty;
+        const int y0 = P.cv.first[oy] - cy0, ny = P.cv.count[oy];
+        const float *hy = P.cv.coeff + (long long)oy * P.cv.widest;
+        float au = 0.0f, av = 0.0f;
+        for (int j = 0; j < ny; ++j) { au = fmaf((float)Uw[(y0 + j) * cpitch + x], hy[j], au); av = fmaf((float)Vw[(y0 + j) * cpitch + x], hy[j], av); }
+        TU[ty * cpitch + x] = au; TV[ty * cpitch + x] = av;
+    }
+    __syncthreads();
+    // horizontal taps + colour conversion: thread -> (row, column), consecutive lanes on consecutive columns
+    for (int u = tid; u < th * YT_W; u += YT_NT) {
+        const int ty = u >> 6, tx = u & 63, ox = ox0 + tx, oy = oy0 + ty;
+        if (tx >= tw) continue;
+        float y = 0.0f, uu = 0.0f, vv = 0.0f;
+        {
+            const int x0 = P.yh.first[ox] - ix0, nx = P.yh.count[ox];
+            const float *hx = P.yh.coeff + (long long)ox * P.yh.widest, *row = TY + ty * ypitch + x0;
+            for (int i = 0; i < nx; ++i) y = fmaf(row[i], hx[i], y);
+        }
+        {
+            const int cx = ox >> 1, x0 = P.ch.first[cx] - cx0, nx = P.ch.count[cx];
+            const float *hx = P.ch.coeff + (long long)cx * P.ch.widest, *ru = TU + ty * cpitch + x0, *rv = TV + ty * cpitch + x0;
+            for (int i = 0; i < nx; ++i) { uu = fmaf(ru[i], hx[i], uu); vv = fmaf(rv[i], hx[i], vv); }
+        }
+        float r, g, b;
+        uu -= 128.0f; vv -= 128.0f;
+        if (P.full_range) { r = y + 1.402f * vv; g = y - 0.344136f * uu - 0.714136f * vv; b = y + 1.772f * uu; }
+        else { const float yl = 1.164383f * (y - 16.0f); r = yl + 1.596027f * vv; g = yl - 0.391762f * uu - 0.812968f * vv; b = yl + 2.017232f * uu; }
+        out[((long long)f * P.out_frame_rows + oy) * P.ow + ox] = pack_rgba(sat8(r), sat8(g), sat8(b), 0xffu);
+    }
+    (void)ncol;
+}
+
 struct BilinearParams { int iw, ih, ow, oh, out_frame_rows, bgra; TriDev h, v; ComposeSpec cs; };
 
 __global__ void __launch_bounds__(256)
@@ -196,6 +288,20 @@ int launch_yuv_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int
         }
         TriUpload up;
         up.add(yh, ow, &td[0]); up.add(yv, oh, &td[1]); up.add(chx, (ow + 1) / 2, &td[2]); up.add(cvy, oh, &td[3]);
+        {   // tile window extents for the tiled kernel
+            auto extent = [](const TriAxis &t, int n, int tile, int align) {
+                int best = 1;
+                for (int a = 0; a < n; a += tile) {
+                    const int b = std::min(n, a + tile) - 1;
+                    const int lo = t.first[a] & ~(align - 1), hi = t.first[b] + t.count[b];
+                    best = std::max(best, hi - lo);
+                }
+                return best;
+            };
+            ctx->yuv_geom[0] = extent(yh, ow, YT_W, 4); ctx->yuv_geom[1] = extent(yv, oh, YT_H, 1);
+            ctx->yuv_geom[2] = extent(chx, (ow + 1) / 2, YT_W / 2, 4); ctx->yuv_geom[3] = extent(cvy, oh, YT_H, 1);
+            ctx->yuv_geom_valid = true;
+        }
         ctx->tri_key[0] = 0;
         B2_TRY(upload_tri(ctx, up));
         const char *base = ctx->tri_tables.as<char>();
@@ -203,6 +309,23 @@ int launch_yuv_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int
         tri_remember(ctx, 1, iw, ih, ow, oh, td, sizeof td);
     }
     P.yh = td[0]; P.yv = td[1]; P.ch = td[2]; P.cv = td[3];
+    if ((iw & 7) == 0 && (reinterpret_cast<uintptr_t>(d_in) & 7) == 0 && !getenv("B200TIMG_YUV_SIMPLE")) {
+        // window extents of a 64 x 32 tile (maxima over tiles), from the host copies of the tables
+        const YuvTileGeom G = ctx->yuv_geom_valid ? YuvTileGeom{ctx->yuv_geom[0], ctx->yuv_geom[1], ctx->yuv_geom[2], ctx->yuv_geom[3]} : YuvTileGeom{0, 0, 0, 0};
+        if (ctx->yuv_geom_valid) {
+            const int nixw = (G.nix + 7) >> 2, ncxw = (G.ncx + 7) >> 2;
+            const size_t bytes = (size_t)G.niy * nixw * 4 + 2 * (size_t)G.ncy * ncxw * 4 + 16 +
+                                 sizeof(float) * ((size_t)YT_H * nixw * 4 + 2 * (size_t)YT_H * ncxw * 4);
+            if (bytes <= 200 * 1024) {
+                B2_CUDA(ctx, cudaFuncSetAttribute(yuv420_rgba_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                B2_KERNEL(ctx, "yuv420_rgba_tiled_kernel");
+                yuv420_rgba_tiled_kernel<<<dim3((ow + YT_W - 1) / YT_W, (oh + YT_H - 1) / YT_H, n_frames), YT_NT, bytes, ctx->stream>>>(
+                    d_in, reinterpret_cast<uint32_t *>(d_out), P, G);
+                B2_LAUNCH_CHECK(ctx);
+                return B200TIMG_OK;
+            }
+        }
+    }
     B2_KERNEL(ctx, "yuv420_rgba_kernel");
     yuv420_rgba_kernel<<<dim3((ow + 31) / 32, (oh + 7) / 8, n_frames), 256, 0, ctx->stream>>>(d_in, reinterpret_cast<uint32_t *>(d_out), P);
     B2_LAUNCH_CHECK(ctx);

@@ -84,6 +84,8 @@ struct b200timg_ctx {
     b200timg::DevBuf tri_tables;   // bilinear / YUV scaler tap tables ...
     int tri_key[5] = {0, 0, 0, 0, 0};          // ... for this (kind, iw, ih, ow, oh), device pointers cached in tri_params
     std::vector<char> tri_params;
+    int yuv_geom[4] = {0, 0, 0, 0};            // window extents of the tiled YUV kernel for the cached geometry
+    bool yuv_geom_valid = false;
     b200timg::DevBuf scale_tmp;    // float4 intermediate + flags of the two-pass scaler (long filters)
     b200timg::DevBuf scale_list;   // work list of tiles the opaque-only scaler hands to the general one
     b200timg::HostBuf pinned;      // staging for sizes / offsets
