@@ -235,6 +235,26 @@ int b200timg_resample_plan(int in_w, int in_h, int out_w, int out_h, int axis, i
                            int *flags, int32_t *first, int32_t *count, int32_t *lead,
                            float *coeff, size_t coeff_cap);
 
+/* ======================= geometry passes around the path ===============
+ * ApplyExifOp (src/jpeg-source.cc:84-119): mirror each row, then rotate by 0, 180, 90 or -90 degrees exactly as
+ * the reference's loops do (90 / -90: out is h x w).  in and out: w*h*4 bytes. */
+int b200timg_exif_op(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, int mirror, int angle, uint8_t *out);
+int b200timg_exif_op_dev(b200timg_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, int w, int h, int mirror, int angle,
+                         int n_frames);
+/* --auto-crop = Magick::Image::trim() (src/graphics-magick-source.cc:238-240; GraphicsMagick is not in the tree:
+ * its documented rule with fuzz 0 is restated, parity unpinned): rect = {x, y, w, h} of the bounding box of the
+ * pixels differing from the corner colours (left and top edges against the top-left pixel, right edge against the
+ * top-right, bottom edge against the bottom-left).  A single-colour image keeps its full size. */
+int b200timg_trim_bbox(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, int rect_xywh[4]);
+/* n_pos windows of dw x dh pixels cut from one w x h image, window k at
+ *     ((x0 + dx*(first_pos + k)) mod w, (y0 + dy*(first_pos + k)) mod h), wrapping around
+ * -- the scroll animation of src/graphics-magick-source.cc:383-389 (one launch for many positions) and, with
+ * n_pos = 1 and dx = dy = 0, a plain crop (--crop-border, :232-237).  out: n_pos * dw*dh*4 bytes. */
+int b200timg_windows(b200timg_ctx *ctx, const uint8_t *img, int w, int h, int dw, int dh, long long x0, long long y0,
+                     int dx, int dy, long long first_pos, int n_pos, uint8_t *out);
+int b200timg_windows_dev(b200timg_ctx *ctx, const uint8_t *d_img, int w, int h, int dw, int dh, long long x0,
+                         long long y0, int dx, int dy, long long first_pos, int n_pos, uint8_t *d_out);
+
 /* ======================= K7: gather of the encoded frames over NCCL ==============================
  * One process per GPU.  The reference is a single process and has no counterpart; frames are
  * independent units, every rank encodes its own batch (b200timg_*_batch_dev) and this call moves the

@@ -74,6 +74,13 @@ ABI = {
                                        C.c_uint32, C.c_int, C.c_int, C.c_int]),
     "b200timg_sixel_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                      C.c_void_p]),
+    "b200timg_exif_op": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]),
+    "b200timg_exif_op_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200timg_trim_bbox": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "b200timg_windows": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_int,
+                                   C.c_int, C.c_longlong, C.c_int, u8p]),
+    "b200timg_windows_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
+                                       C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
     "b200timg_gather_unique_id": (C.c_int, [C.c_char_p]),
     "b200timg_gather_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "b200timg_gather_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
@@ -197,6 +204,27 @@ class Context:
         assert yuv.size == iw * ih * 3 // 2
         out = np.empty((oh, ow, 4), np.uint8)
         self._chk(lib().b200timg_yuv_scale(self.h, _np_ptr(yuv), iw, ih, fmt, _np_ptr(out), ow, oh))
+        return out
+
+    def exif_op(self, fb, mirror=False, angle=0):
+        fb = np.ascontiguousarray(fb, dtype=np.uint8)
+        h, w = fb.shape[:2]
+        out = np.empty((w, h, 4) if angle in (90, -90) else (h, w, 4), np.uint8)
+        self._chk(lib().b200timg_exif_op(self.h, _np_ptr(fb), w, h, int(mirror), angle, _np_ptr(out)))
+        return out
+
+    def trim_bbox(self, fb):
+        fb = np.ascontiguousarray(fb, dtype=np.uint8)
+        h, w = fb.shape[:2]
+        r = (C.c_int * 4)()
+        self._chk(lib().b200timg_trim_bbox(self.h, _np_ptr(fb), w, h, r))
+        return tuple(r)
+
+    def windows(self, img, dw, dh, x0=0, y0=0, dx=0, dy=0, first_pos=0, n_pos=1):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape[:2]
+        out = np.empty((n_pos, dh, dw, 4), np.uint8)
+        self._chk(lib().b200timg_windows(self.h, _np_ptr(img), w, h, dw, dh, x0, y0, dx, dy, first_pos, n_pos, _np_ptr(out)))
         return out
 
     def compose_bg(self, fb, bg, pattern=0, pw=0, ph=0, start_row=0, has_bg=True):
