@@ -255,6 +255,21 @@ int b200timg_windows(b200timg_ctx *ctx, const uint8_t *img, int w, int h, int dw
 int b200timg_windows_dev(b200timg_ctx *ctx, const uint8_t *d_img, int w, int h, int dw, int dh, long long x0,
                          long long y0, int dx, int dy, long long first_pos, int n_pos, uint8_t *d_out);
 
+/* ======================= Kitty / iTerm2 canvases: PNG + base64 ===================
+ * png::Encode (src/timg-png.cc:90-152): signature, IHDR, one IDAT holding the zlib stream of the scanlines (each
+ * row filtered with "Sub"), IEND.  rgb24 != 0: colour type 2 (png::ColorEncoding::kRGB_24), else RGBA.  The
+ * reference deflates with libdeflate (third party, not in its tree); this stream uses stored deflate blocks, so it
+ * decodes to the same pixels but is not the same bytes, and its size is exactly b200timg_png_size().
+ * EncodeBase64 (src/timg-base64.h:28-53) of the file goes to b64 when given.  The protocol framing
+ * (src/kitty-canvas.cc:196-226, src/iterm2-canvas.cc:66-72) stays in the host adapter. */
+size_t b200timg_png_size(int w, int h, int rgb24);
+size_t b200timg_base64_size(size_t n_bytes);
+int b200timg_png_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h, int rgb24, uint8_t *out, size_t cap,
+                        char *b64, size_t b64_cap);
+/* n device-resident frames -> n files at d_png + f*png_size (and their base64 at d_b64 + f*base64_size, or NULL) */
+int b200timg_png_batch_dev(b200timg_ctx *ctx, const uint8_t *d_frames, int w, int h, int n_frames, int rgb24,
+                           uint8_t *d_png, char *d_b64);
+
 /* ======================= K7: gather of the encoded frames over NCCL ==============================
  * One process per GPU.  The reference is a single process and has no counterpart; frames are
  * independent units, every rank encodes its own batch (b200timg_*_batch_dev) and this call moves the
