@@ -10,13 +10,18 @@
 //   B200BlockCanvas  : timg::TerminalCanvas    (src/terminal-canvas.h:28-60), replaces
 //                                              UnicodeBlockCanvas (src/unicode-block-canvas.h:33-80)
 //   B200SixelCanvas  : timg::TerminalCanvas,   replaces SixelCanvas (src/sixel-canvas.h:29-47)
+//   B200ITerm2Canvas / B200KittyCanvas : timg::TerminalCanvas, replace ITerm2GraphicsCanvas / KittyGraphicsCanvas
+//                                              (src/iterm2-canvas.h, src/kitty-canvas.h; no tmux passthrough)
 //
 // Ownership follows the reference: the OutBuffer handed to the write sequencer holds
 // a `new char[]` that the writer thread frees; the input Framebuffer is only borrowed during Send.
 #ifndef B200TIMG_ADAPTERS_H
 #define B200TIMG_ADAPTERS_H
 
+#include <cassert>
 #include <cstdio>
+#include <ctime>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -208,6 +213,98 @@ private:
     const DisplayOptions &options_;
     const bool full_cell_jump_;
     const char *before_, *after_;
+};
+
+// ---- ITerm2GraphicsCanvas / KittyGraphicsCanvas -------------------------------------------------
+// The PNG file and its base64 text come from the device (b200timg_png_encode); the protocol framing is the
+// reference's, byte for byte (src/iterm2-canvas.cc:66-72, src/kitty-canvas.cc:196-226 without the tmux
+// passthrough variant, which only wraps the same chunks).  The PNG itself uses stored deflate blocks, so the
+// base64 payload is larger than libdeflate's but decodes to the same pixels.
+class B200ITerm2Canvas final : public TerminalCanvas {
+public:
+    B200ITerm2Canvas(BufferedWriteSequencer *ws, const DisplayOptions &opts) : TerminalCanvas(ws), options_(opts) {}
+    int cell_height_for_pixels(int pixels) const final {                                // src/iterm2-canvas.cc:91-95
+        assert(pixels <= 0);
+        return -((-pixels + options_.cell_y_px - 1) / options_.cell_y_px);
+    }
+    void Send(int x, int dy, const Framebuffer &fb, SeqType seq_type, Duration end_of_frame) override {
+        if (dy < 0) MoveCursorDY(cell_height_for_pixels(dy));
+        MoveCursorDX(x / options_.cell_x_px);
+        const int w = fb.width(), h = fb.height(), rgb24 = options_.local_alpha_handling ? 1 : 0;
+        const size_t png_size = b200timg_png_size(w, h, rgb24), b64_size = b200timg_base64_size(png_size);
+        std::unique_ptr<uint8_t[]> png(new uint8_t[png_size]);
+        char *buffer = new char[b64_size + 4096];
+        char *pos = AppendPrefixToBuffer(buffer);
+        pos += sprintf(pos, "\033]1337;File=size=%d;width=%dpx;height=%dpx;inline=1:", (int)png_size, w, h);   // .cc:66-68
+        {
+            std::lock_guard<std::mutex> l(B200Context::Lock());
+            B200Context::Check(b200timg_png_encode(B200Context::Get(), (const uint8_t *)fb.begin(), w, h, rgb24, png.get(), png_size,
+                                                   pos, b64_size), "png_encode");
+        }
+        pos += b64_size;
+        *pos++ = '\007';
+        *pos++ = '\n';                                                                   // .cc:71-72
+        write_sequencer_->WriteBuffer(OutBuffer(buffer, (size_t)(pos - buffer)), seq_type, end_of_frame);
+    }
+
+private:
+    const DisplayOptions &options_;
+};
+
+class B200KittyCanvas final : public TerminalCanvas {
+public:
+    B200KittyCanvas(BufferedWriteSequencer *ws, const DisplayOptions &opts) : TerminalCanvas(ws), options_(opts) {}
+    int cell_height_for_pixels(int pixels) const final {                                // src/kitty-canvas.cc:248-252
+        assert(pixels <= 0);
+        return -((-pixels + options_.cell_y_px - 1) / options_.cell_y_px);
+    }
+    void Send(int x, int dy, const Framebuffer &fb, SeqType seq_type, Duration end_of_frame) override {
+        if (dy < 0) MoveCursorDY(cell_height_for_pixels(dy));
+        MoveCursorDX(x / options_.cell_x_px);
+        uint32_t id = 0;                                                                 // .cc:142-172
+        switch (seq_type) {
+        case SeqType::FrameImmediate: id = CreateId(); break;
+        case SeqType::StartOfAnimation: id = CreateId(); CreateId(); animation_id_ = id; flip_buffer_ = 0; break;
+        case SeqType::AnimationFrame: ++flip_buffer_; id = animation_id_ + (flip_buffer_ % 2); break;
+        case SeqType::ControlWrite: break;
+        }
+        const int w = fb.width(), h = fb.height(), rgb24 = options_.local_alpha_handling ? 1 : 0;
+        int png_size = (int)b200timg_png_size(w, h, rgb24);
+        const size_t b64_size = b200timg_base64_size((size_t)png_size);
+        std::unique_ptr<uint8_t[]> png(new uint8_t[(size_t)png_size]);
+        std::unique_ptr<char[]> b64(new char[b64_size]);
+        {
+            std::lock_guard<std::mutex> l(B200Context::Lock());
+            B200Context::Check(b200timg_png_encode(B200Context::Get(), (const uint8_t *)fb.begin(), w, h, rgb24, png.get(), (size_t)png_size,
+                                                   b64.get(), b64_size), "png_encode");
+        }
+        constexpr int kChunk = 4096, kByteChunk = kChunk / 4 * 3;                        // .cc:43-44
+        char *buffer = new char[b64_size + (b64_size / kChunk + 2) * 32 + 4096];
+        char *pos = AppendPrefixToBuffer(buffer);
+        pos += sprintf(pos, "\033_Ga=T,i=%u,q=2,f=100,m=%d;", id, png_size > kByteChunk);   // .cc:197-203
+        const char *src = b64.get();
+        while (png_size) {                                                               // .cc:206-219: chunks of <= 4096 base64 characters
+            const int chunk_bytes = std::min(png_size, kByteChunk);
+            const size_t chars = (size_t)(chunk_bytes + 2) / 3 * 4;                      // every chunk but the last is a multiple of 3 bytes
+            memcpy(pos, src, chars); pos += chars; src += chars;
+            png_size -= chunk_bytes;
+            if (png_size) pos += sprintf(pos, "\033\\\033_Gq=2,m=%d;", png_size > kByteChunk);
+        }
+        *pos++ = '\033'; *pos++ = '\\';                                                  // .cc:220
+        *pos++ = '\n';                                                                   // .cc:227
+        write_sequencer_->WriteBuffer(OutBuffer(buffer, (size_t)(pos - buffer)), seq_type, end_of_frame);
+    }
+
+private:
+    static uint32_t CreateId() {                                                         // .cc:48-53
+        static const uint32_t kStart = (uint32_t)time(nullptr) << 7;
+        static uint32_t counter = 0;
+        counter++;
+        return kStart + counter;
+    }
+    const DisplayOptions &options_;
+    uint32_t animation_id_ = 0;
+    uint8_t flip_buffer_ = 0;
 };
 
 }  // namespace timg

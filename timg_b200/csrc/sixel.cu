@@ -378,14 +378,15 @@ sixel_lut_kernel(SixelWork W) {
     __syncthreads();
     const int n = (int)hdr->ncolors;
     const uint32_t cell = blockIdx.x * 256 + threadIdx.x;
-    const int r = (int)(((cell >> 10) & 31) << 3 | 4), g = (int)(((cell >> 5) & 31) << 3 | 4), b = (int)((cell & 31) << 3 | 4);
-    int best = 0x7fffffff, bi = 0;
+    // centre of the cell as packed bytes; squared distance = dot(|d|, |d|) with d the per-byte absolute difference
+    // (VABSDIFF4 + IDP.4A); "first minimum" = minimum of (distance << 8 | index)
+    const uint32_t c = (((cell >> 10) & 31) << 3 | 4) | ((((cell >> 5) & 31) << 3 | 4) << 8) | (((cell & 31) << 3 | 4) << 16);
+    uint32_t best = 0xffffffffu;
     for (int i = 0; i < n; ++i) {
-        const uint32_t p = s_pal[i];
-        const int dr = r - (int)(p & 0xff), dg = g - (int)((p >> 8) & 0xff), db = b - (int)((p >> 16) & 0xff);
-        const int d = dr * dr + dg * dg + db * db;
-        if (d < best) { best = d; bi = i; }
+        const uint32_t d = __vabsdiffu4(c, s_pal[i]);
+        best = min(best, (__dp4a(d, d, 0u) << 8) | (uint32_t)i);
     }
+    const uint32_t bi = n > 0 ? (best & 255u) : 0u;
     W.lut[(long long)f * 32768 + cell] = (uint8_t)bi;
 }
 

@@ -273,6 +273,15 @@ static inline unsigned __viaddmin_s16x2_relu(unsigned a, unsigned b, unsigned c)
     }
     return r;
 }
+static inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k) { const int x = (a >> (8 * k)) & 255, y = (b >> (8 * k)) & 255; r |= (unsigned)(x > y ? x - y : y - x) << (8 * k); }
+    return r;
+}
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+    for (int k = 0; k < 4; ++k) c += ((a >> (8 * k)) & 255) * ((b >> (8 * k)) & 255);
+    return c;
+}
 static inline unsigned __vadd2(unsigned a, unsigned b) { return (((a & 0xffff) + (b & 0xffff)) & 0xffff) | (((a >> 16) + (b >> 16)) << 16); }
 static inline unsigned __vsub2(unsigned a, unsigned b) { return (((a & 0xffff) - (b & 0xffff)) & 0xffff) | (((a >> 16) - (b >> 16)) << 16); }
 
