@@ -74,6 +74,10 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     ctx->tables.release(); ctx->sixel_work.release(); ctx->misc.release(); ctx->scale_list.release(); ctx->scale_tmp.release(); ctx->tri_tables.release();
     ctx->pinned.release(); ctx->pinned_io.release();
     for (int i = 0; i < 2; ++i) { ctx->pipe_in[i].release(); ctx->pipe_out[i].release(); }
+    if (ctx->parts_ready) {
+        for (int i = 0; i < 4; ++i) { cudaStreamSynchronize(ctx->part_stream[i]); cudaStreamDestroy(ctx->part_stream[i]); cudaEventDestroy(ctx->ev_part[i]); }
+        cudaEventDestroy(ctx->ev_fork);
+    }
     if (ctx->pipe_ready) {
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_up[i]); cudaEventDestroy(ctx->ev_write[i]); cudaEventDestroy(ctx->ev_d2h[i]); cudaEventDestroy(ctx->ev_scaled[i]); }
         cudaEventDestroy(ctx->ev_prep);
@@ -411,32 +415,82 @@ int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const 
                          b->x_indent_cells, d_out, out_cap, d_offsets);
 }
 
-static int sixel_batch_phases(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,
-                              char *d_out, size_t out_cap, uint64_t *d_offsets, int phases) {
-    if (phases == 2) {   // scaled frames are still in ctx->fb_scaled from the prepare phase
-        return launch_sixel(ctx, ctx->fb_scaled.as<uint8_t>(), b->out_w, round_to_sixel(b->out_h), b->n_frames, d_out,
-                            out_cap, d_offsets, 2);
-    }
-    // SixelCanvas::Send (src/sixel-canvas.cc:109-120): pad to a multiple of 6 rows with
-    // transparent pixels, compose the background into the pad strip only, keep the rest.
+// One slice of a sixel batch: scale (+ fused compose), pad strip, then the per-frame front kernels.
+static int sixel_slice_front(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src, int f0, int n, bool reserve) {
     const int hp = round_to_sixel(b->out_h);
     const size_t frame_bytes = (size_t)b->out_w * hp * 4;
-    ctx->resident_fb = nullptr;
-    B2_CUDA(ctx, ctx->fb_scaled.reserve(frame_bytes * b->n_frames));
-    uint8_t *d_fb = ctx->fb_scaled.as<uint8_t>();
+    uint8_t *d_fb_all = ctx->fb_scaled.as<uint8_t>(), *d_fb = d_fb_all + (size_t)f0 * frame_bytes;
     // scale with AlphaComposeBackground fused into the epilogue (what the sources do, e.g.
     // src/stb-image-source.cc:56-60); then only the pad strip is cleared and composed, exactly the
     // canvas' own start_row = height call (src/sixel-canvas.cc:115-118).
     const ComposeSpec cs = make_compose_spec(b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h);
-    B2_TRY(batch_scale(ctx, b, d_src, d_fb, hp, &cs));
+    b200timg_batch sub = *b;
+    sub.n_frames = n;
+    B2_TRY(batch_scale(ctx, &sub, d_src + (size_t)f0 * src_frame_bytes(b), d_fb, hp, &cs));
     if (ctx->ev_after_scale) B2_CUDA(ctx, cudaEventRecord(ctx->ev_after_scale, ctx->stream));
     if (hp != b->out_h) {
         B2_CUDA(ctx, cudaMemset2DAsync(d_fb + (size_t)b->out_h * b->out_w * 4, frame_bytes, 0,
-                                       (size_t)(hp - b->out_h) * b->out_w * 4, b->n_frames, ctx->stream));
-        B2_TRY(launch_compose(ctx, d_fb, b->out_w, hp, b->n_frames, b->has_bg, b->bg, b->pattern, b->pattern_w,
-                              b->pattern_h, b->out_h));
+                                       (size_t)(hp - b->out_h) * b->out_w * 4, n, ctx->stream));
+        B2_TRY(launch_compose(ctx, d_fb, b->out_w, hp, n, b->has_bg, b->bg, b->pattern, b->pattern_w, b->pattern_h, b->out_h));
     }
-    return launch_sixel(ctx, d_fb, b->out_w, hp, b->n_frames, d_out, out_cap, d_offsets, phases);
+    return launch_sixel_front(ctx, d_fb_all, b->out_w, hp, b->n_frames, f0, n, reserve);
+}
+
+static int parts_init(b200timg_ctx *ctx) {
+    if (ctx->parts_ready) return B200TIMG_OK;
+    for (int i = 0; i < 4; ++i) {
+        B2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->part_stream[i], cudaStreamNonBlocking));
+        B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_part[i], cudaEventDisableTiming));
+    }
+    B2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    ctx->parts_ready = true;
+    return B200TIMG_OK;
+}
+
+static int sixel_batch_phases(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,
+                              char *d_out, size_t out_cap, uint64_t *d_offsets, int phases) {
+    const int hp = round_to_sixel(b->out_h);
+    if (phases == 2)     // scaled frames are still in ctx->fb_scaled from the prepare phase
+        return launch_sixel_back(ctx, b->out_w, hp, b->n_frames, d_out, out_cap, d_offsets, 2);
+    // SixelCanvas::Send (src/sixel-canvas.cc:109-120): pad to a multiple of 6 rows with
+    // transparent pixels, compose the background into the pad strip only, keep the rest.
+    const size_t frame_bytes = (size_t)b->out_w * hp * 4;
+    ctx->resident_fb = nullptr;
+    B2_CUDA(ctx, ctx->fb_scaled.reserve(frame_bytes * b->n_frames));
+    // Large device-resident batches run as slices on separate streams: the palette and dither kernels of a slice are
+    // latency-bound (one CTA per frame), so the scaler and the emitter of the other slices fill the machine meanwhile.
+    // Timing runs (b200timg_profile) keep the plain in-order chain so that per-kernel durations stay meaningful.
+    int parts = 1;
+    if (phases == 3 && !ctx->profiling && !ctx->ev_after_scale && b->n_frames >= 32) parts = b->n_frames >= 512 ? 4 : 2;
+    if (const char *e = getenv("B200TIMG_PARTS")) parts = std::max(1, std::min(4, std::min(atoi(e), b->n_frames)));
+    if (parts == 1) {
+        B2_TRY(sixel_slice_front(ctx, b, d_src, 0, b->n_frames, true));
+        return launch_sixel_back(ctx, b->out_w, hp, b->n_frames, d_out, out_cap, d_offsets, phases);
+    }
+    B2_TRY(parts_init(ctx));
+    cudaStream_t main_stream = ctx->stream;
+    const int per = (b->n_frames + parts - 1) / parts;
+    // everything a slice would allocate is sized for the whole batch first: nothing may be re-allocated while slices run
+    ctx->part_slots = parts; ctx->part_max_frames = per;
+    B2_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+    int rc = B200TIMG_OK;
+    for (int k = 0; k < parts && rc == B200TIMG_OK; ++k) {
+        const int f0 = k * per, n = std::min(per, b->n_frames - f0);
+        if (n <= 0) break;
+        ctx->stream = ctx->part_stream[k];
+        ctx->part_slot = k;
+        if (cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0) != cudaSuccess) rc = ctx->fail(B200TIMG_ECUDA, "batch: stream wait failed");
+        if (rc == B200TIMG_OK) rc = sixel_slice_front(ctx, b, d_src, f0, n, k == 0);
+        if (rc == B200TIMG_OK && cudaEventRecord(ctx->ev_part[k], ctx->stream) != cudaSuccess) rc = ctx->fail(B200TIMG_ECUDA, "batch: event record failed");
+        if (rc == B200TIMG_OK && cudaStreamWaitEvent(main_stream, ctx->ev_part[k], 0) != cudaSuccess) rc = ctx->fail(B200TIMG_ECUDA, "batch: stream wait failed");
+    }
+    ctx->stream = main_stream;
+    ctx->part_slot = 0; ctx->part_slots = 1; ctx->part_max_frames = 0;
+    if (rc != B200TIMG_OK) {                       // leave no slice running behind the caller's back
+        for (int k = 0; k < parts; ++k) cudaStreamSynchronize(ctx->part_stream[k]);
+        return rc;
+    }
+    return launch_sixel_back(ctx, b->out_w, hp, b->n_frames, d_out, out_cap, d_offsets, phases);
 }
 
 int b200timg_sixel_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b, const uint8_t *d_src,

@@ -96,6 +96,11 @@ struct b200timg_ctx {
     cudaEvent_t ev_after_scale = nullptr;      // set by the host pipeline: recorded right after the scaler of a batch call
     b200timg::DevBuf pipe_in[2], pipe_out[2];
     bool pipe_ready = false;
+    // slices of a large device-resident batch on their own streams (api.cu: sixel_batch_phases)
+    cudaStream_t part_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_part[4] = {nullptr, nullptr, nullptr, nullptr}, ev_fork = nullptr;
+    bool parts_ready = false;
+    int part_slot = 0, part_slots = 1, part_max_frames = 0;   // which slice is being launched / how many / frames per slice
     bool sixel_attrs_set = false;            // cudaFuncSetAttribute done for this context's device
     // K7 gather (gather.cu): NCCL communicator (owned or attached), its stream and ordering events
     void *nccl_comm = nullptr;
@@ -234,6 +239,8 @@ int launch_yuv_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int
                      int out_frame_rows, int n_frames);
 int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
                  size_t out_cap, uint64_t *d_offsets, int phases);
+int launch_sixel_front(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_total, int f0, int n, bool reserve);
+int launch_sixel_back(b200timg_ctx *ctx, int w, int h, int n_frames, char *d_out, size_t out_cap, uint64_t *d_offsets, int phases);
 int sixel_debug_fetch(b200timg_ctx *ctx, uint32_t *h_palette, uint32_t *h_counts, uint8_t *h_index, size_t index_bytes);
 
 }  // namespace b200timg

@@ -1280,7 +1280,10 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
             const int sp3 = (nix3 + 3) & ~3, tp3 = sp3 | 1;
             const size_t v3smem = sizeof(uint32_t) * (size_t)niy * sp3 + (sizeof(float2) + sizeof(float)) * (size_t)V3_TH * tp3 + 16 +
                                   sizeof(float) * ((size_t)V3_TW * 8 + V3_TH * 8) + sizeof(int) * (V3_TW + V3_TH);
-            const bool v3_ok = planar_ok && !getenv("B200TIMG_NO_V3") && v3smem <= 100 * 1024 && (size_t)V3_TH * (V3_TW + 1) <= (size_t)niy * sp3;
+            // v3 pays off in the FAST arithmetic (5.4 vs 7.9 ms per 148 C2 frames); in EXACT arithmetic its streaming passes are
+            // slower than the planar kernel (9.3 vs 7.9 ms), so bit-exact scaling stays on the planar kernel unless asked
+            const bool v3_ok = planar_ok && !getenv("B200TIMG_NO_V3") && (fast || getenv("B200TIMG_V3_EXACT")) && v3smem <= 100 * 1024 &&
+                               (size_t)V3_TH * (V3_TW + 1) <= (size_t)niy * sp3;
             if (planar_ok) {
                 B2_CUDA(ctx, ctx->misc.reserve(4096 + sizeof(int32_t) * (size_t)(ntx + nty + ntx3)));
                 int32_t *d_t = reinterpret_cast<int32_t *>(ctx->misc.as<char>() + 4096);
@@ -1289,9 +1292,10 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
                 B2_CUDA(ctx, cudaMemcpyAsync(d_t + ntx + nty, tix3.data(), sizeof(int32_t) * ntx3, cudaMemcpyHostToDevice, ctx->stream));
                 PlanarGeom PG{nix, niy, sp, tp, (unsigned)(0x100000000ull / (unsigned)(sp / 4)) + 1u, d_t, d_t + ntx};
                 if (v3_ok) {
-                    const size_t list_bytes = sizeof(uint32_t) * (1 + 3 * (size_t)ntx3 * nty * n_frames);
-                    B2_CUDA(ctx, ctx->scale_list.reserve(list_bytes));
-                    uint32_t *d_list = ctx->scale_list.as<uint32_t>();
+                    // one work list per concurrently running slice of a batch (api.cu), sized before any slice starts
+                    const size_t list_words = 1 + 3 * (size_t)ntx3 * nty * (size_t)std::max(n_frames, ctx->part_max_frames);
+                    B2_CUDA(ctx, ctx->scale_list.reserve(sizeof(uint32_t) * list_words * (size_t)ctx->part_slots));
+                    uint32_t *d_list = ctx->scale_list.as<uint32_t>() + list_words * (size_t)ctx->part_slot;
                     B2_CUDA(ctx, cudaMemsetAsync(d_list, 0, sizeof(uint32_t), ctx->stream));
                     V3Geom VG{nix3, niy, sp3, tp3, (unsigned)(0x100000000ull / (unsigned)(sp3 / 4)) + 1u, d_t + ntx + nty, d_t + ntx, d_list};
                     V3Fn fn = fast ? v3_h<false>(hc, vc) : v3_h<true>(hc, vc);

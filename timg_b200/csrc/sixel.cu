@@ -817,17 +817,27 @@ sixel_compact_kernel(int w, int h, SixelWork W, const uint64_t *__restrict__ off
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// phases: 1 = everything up to and including the frame offsets (sizes known, nothing written),
-//         2 = write the bytes.  3 = both, back to back without a host round trip.
-int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
-                 size_t out_cap, uint64_t *d_offsets, int phases) {
+// ---- host side ------------------------------------------------------------------------------------
+// The chain of a batch is  front (per frame: palette, table, dither, band sizes)  ->  back (sizes -> offsets ->
+// bytes in their final place).  The front part can be run for SLICES of the batch on different streams
+// (launch_sixel_front with f0 / n): a batch pipeline overlaps the latency-bound per-frame kernels of one
+// slice with the scaler of the next.
+struct SixelPlan {
+    SixelWork W;
+    bool emit_v1, dither_v1;
+    EmitGeom G;
+    size_t emit_smem, o_d2_bnd, o_d2_prog;
+    long long npix;
+};
+
+static int sixel_plan(b200timg_ctx *ctx, int w, int h, int n_frames, bool reserve, SixelPlan *S) {
     if (h % 6) return ctx->fail(B200TIMG_EINVAL, "sixel: height %d is not a multiple of 6", h);
-    if ((reinterpret_cast<uintptr_t>(d_fb) & 3)) return ctx->fail(B200TIMG_EINVAL, "sixel: framebuffer must be 4-byte aligned");
     if (n_frames > 65535) return ctx->fail(B200TIMG_EINVAL, "sixel: too many frames for one launch");
+    SixelWork &W = S->W;
     const long long npix = (long long)w * h;
+    S->npix = npix;
     long long step_px = npix / 18383; if (npix < 18383) step_px = 6; if (step_px == 0) step_px = 1;
     const long long ns = (npix + step_px - 1) / step_px;
-    SixelWork W;
     W.ent_cap = (int)std::min<long long>(32768, ns);
     W.nb32 = (h + 31) / 32; W.nbands = h / 6;
     if (W.nb32 > 2048) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too tall");
@@ -846,14 +856,14 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     const size_t o_scr = off;
     // two emitters: v1 (per-band sizes into a scratch arena + compaction kernel; <= 4095 px wide) and the single-pass v2
     // (sixel_emit.cu: any width, no arena).  v2 is used where v1 cannot go and when B200TIMG_EMIT_V2 is set.
-    const bool emit_v1 = !getenv("B200TIMG_EMIT_V2") && w <= 4095 && sizeof(uint32_t) * (size_t)6 * w <= (size_t)(227 - 36) * 1024;
-    if (emit_v1) off += W.band_cap * W.nbands * n_frames;
-    const bool dither_v1 = getenv("B200TIMG_DITHER_V1") != nullptr; // round-1 ditherer, kept for A/B runs
+    S->emit_v1 = !getenv("B200TIMG_EMIT_V2") && w <= 4095 && sizeof(uint32_t) * (size_t)6 * w <= (size_t)(227 - 36) * 1024;
+    if (S->emit_v1) off += W.band_cap * W.nbands * n_frames;
+    S->dither_v1 = getenv("B200TIMG_DITHER_V1") != nullptr;      // round-1 ditherer, kept for A/B runs
     size_t d_bnd, d_prog;
     const size_t o_d2 = off; off += sixel_dither_workspace(w, h, n_frames, &d_bnd, &d_prog);
     size_t e_hdr, e_desc, e_ctl;
     const size_t o_e2 = off; off += sixel_emit_workspace(w, h, n_frames, &e_hdr, &e_desc, &e_ctl);
-    if (phases & 1) B2_CUDA(ctx, ctx->sixel_work.reserve(off));
+    if (reserve) B2_CUDA(ctx, ctx->sixel_work.reserve(off));
     if (!ctx->sixel_work.p || ctx->sixel_work.cap < off) return ctx->fail(B200TIMG_EINVAL, "sixel: write phase without prepare");
     ctx->sixel_idx_off = o_idx;
     char *base = ctx->sixel_work.as<char>();
@@ -865,63 +875,83 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     W.hdr_bytes = base + o_e2 + e_hdr;
     W.desc = reinterpret_cast<unsigned long long *>(base + o_e2 + e_desc);
     W.ctl = reinterpret_cast<uint32_t *>(base + o_e2 + e_ctl);
-    const uint32_t *fb = reinterpret_cast<const uint32_t *>(d_fb);
-
-    EmitGeom G; G.w = w; G.h = h; G.cols_per_warp = ((w + EW - 1) / EW + 31) / 32 * 32;
+    S->o_d2_bnd = o_d2 + d_bnd; S->o_d2_prog = o_d2 + d_prog;
+    S->G.w = w; S->G.h = h; S->G.cols_per_warp = ((w + EW - 1) / EW + 31) / 32 * 32;
     const size_t smem_limit = 227 * 1024 - 36 * 1024;   // the emit kernel also has ~33 KB of static shared memory
-    const size_t emit_smem = sizeof(uint32_t) * (size_t)6 * w;
-    if (emit_v1 && (w > 4095 || emit_smem > smem_limit)) return ctx->fail(B200TIMG_EINVAL, "sixel: frame too wide (%d > 4095)", w);
+    S->emit_smem = sizeof(uint32_t) * (size_t)6 * w;
     if (!ctx->sixel_attrs_set) {                         // function attributes are per device, i.e. per context
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + DW_MAX * DWARP_SMEM));
+        const size_t t_words = W.ent_cap > 16384 ? (size_t)W.ent_cap : 16384;
+        const size_t smem_tables = sizeof(uint32_t) * (t_words + (size_t)W.ent_cap);
+        if (smem_tables <= 200 * 1024)
+            B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ctx->sixel_attrs_set = true;
     }
-    const dim3 egrid(W.nbands, n_frames);
-    if (phases & 1) {
-        B2_KERNEL(ctx, "sixel_palette_kernel");
-        {
-            const size_t t_words = W.ent_cap > 16384 ? (size_t)W.ent_cap : 16384;
-            const size_t smem_tables = sizeof(uint32_t) * (t_words + (size_t)W.ent_cap);
-            if (smem_tables <= 200 * 1024) {
-                B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
-                sixel_palette_kernel<true><<<n_frames, PT, smem_tables, ctx->stream>>>(fb, w, h, W);
-            } else {
-                sixel_palette_kernel<false><<<n_frames, PT, 65536, ctx->stream>>>(fb, w, h, W);
-            }
-        }
-        B2_LAUNCH_CHECK(ctx);
-        B2_KERNEL(ctx, "sixel_lut_kernel");
-        sixel_lut_kernel<<<dim3(128, n_frames), 256, 0, ctx->stream>>>(W);
-        B2_LAUNCH_CHECK(ctx);
-        {
-            long long blocks = (npix + 255) / 256; if (blocks > 64) blocks = 64;
-            B2_KERNEL(ctx, "sixel_map_kernel");
-            sixel_map_kernel<<<dim3((unsigned)blocks, n_frames), 256, 0, ctx->stream>>>(fb, npix, W);
-            B2_LAUNCH_CHECK(ctx);
-        }
-        if (!dither_v1) {
-            B2_TRY(launch_sixel_dither(ctx, fb, w, h, n_frames, W, base + o_d2 + d_bnd, base + o_d2 + d_prog));
-        } else {
-        B2_KERNEL(ctx, "sixel_dither_kernel");
-        {
-            // warps per frame: as many as fit, but in full rounds over the 32-row bands
-            const int rounds = (W.nb32 + DW_MAX - 1) / DW_MAX;
-            const int nwarps = (W.nb32 + rounds - 1) / rounds;
-            const size_t dsmem = 32768 + (size_t)nwarps * DWARP_SMEM;
-            sixel_dither_kernel<<<n_frames, nwarps * 32, dsmem, ctx->stream>>>(fb, w, h, nwarps, W);
-        }
-        B2_LAUNCH_CHECK(ctx);
-        }
+    return B200TIMG_OK;
+}
+
+// frames [f0, f0 + n) of a batch of n_total: palette -> table -> (map | dither) -> band sizes (v1 emitter), on ctx->stream
+int launch_sixel_front(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_total, int f0, int n, bool reserve) {
+    if ((reinterpret_cast<uintptr_t>(d_fb) & 3)) return ctx->fail(B200TIMG_EINVAL, "sixel: framebuffer must be 4-byte aligned");
+    SixelPlan S;
+    B2_TRY(sixel_plan(ctx, w, h, n_total, reserve, &S));
+    SixelWork W = S.W;                                    // the slice's view of the per-frame arrays
+    const long long npix = S.npix;
+    W.hdr += f0; W.ent_a += (long long)f0 * W.ent_cap; W.ent_b += (long long)f0 * W.ent_cap; W.lut += (long long)f0 * 32768;
+    W.index += (long long)f0 * npix; W.boundary += (long long)f0 * W.nb32 * w;
+    W.band_bytes += (long long)f0 * W.nbands; W.band_off += (long long)f0 * W.nbands;
+    W.scratch += (size_t)f0 * W.nbands * W.band_cap;
+    const uint32_t *fb = reinterpret_cast<const uint32_t *>(d_fb) + (long long)f0 * npix;
+    char *base = ctx->sixel_work.as<char>();
+    B2_KERNEL(ctx, "sixel_palette_kernel");
+    {
+        const size_t t_words = W.ent_cap > 16384 ? (size_t)W.ent_cap : 16384;
+        const size_t smem_tables = sizeof(uint32_t) * (t_words + (size_t)W.ent_cap);
+        if (smem_tables <= 200 * 1024) sixel_palette_kernel<true><<<n, PT, smem_tables, ctx->stream>>>(fb, w, h, W);
+        else sixel_palette_kernel<false><<<n, PT, 65536, ctx->stream>>>(fb, w, h, W);
     }
-    if (!emit_v1) {
+    B2_LAUNCH_CHECK(ctx);
+    B2_KERNEL(ctx, "sixel_lut_kernel");
+    sixel_lut_kernel<<<dim3(128, n), 256, 0, ctx->stream>>>(W);
+    B2_LAUNCH_CHECK(ctx);
+    {
+        long long blocks = (npix + 255) / 256; if (blocks > 64) blocks = 64;
+        B2_KERNEL(ctx, "sixel_map_kernel");
+        sixel_map_kernel<<<dim3((unsigned)blocks, n), 256, 0, ctx->stream>>>(fb, npix, W);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    if (!S.dither_v1) {
+        B2_TRY(launch_sixel_dither(ctx, fb, w, h, n, n_total, W, base + S.o_d2_bnd + sizeof(uint4) * (size_t)f0 * W.nb32 * w,
+                                   base + S.o_d2_prog + sizeof(int) * (size_t)f0 * W.nb32));
+    } else {
+        B2_KERNEL(ctx, "sixel_dither_kernel");
+        // warps per frame: as many as fit, but in full rounds over the 32-row bands
+        const int rounds = (W.nb32 + DW_MAX - 1) / DW_MAX;
+        const int nwarps = (W.nb32 + rounds - 1) / rounds;
+        const size_t dsmem = 32768 + (size_t)nwarps * DWARP_SMEM;
+        sixel_dither_kernel<<<n, nwarps * 32, dsmem, ctx->stream>>>(fb, w, h, nwarps, W);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    if (S.emit_v1) {
+        B2_KERNEL(ctx, "sixel_emit_kernel");
+        sixel_emit_kernel<<<dim3(W.nbands, n), ET, S.emit_smem, ctx->stream>>>(S.G, W);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    return B200TIMG_OK;
+}
+
+// the whole batch: sizes -> offsets (phase 1), bytes into d_out (phase 2)
+int launch_sixel_back(b200timg_ctx *ctx, int w, int h, int n_frames, char *d_out, size_t out_cap, uint64_t *d_offsets, int phases) {
+    SixelPlan S;
+    B2_TRY(sixel_plan(ctx, w, h, n_frames, false, &S));
+    const SixelWork &W = S.W;
+    if (!S.emit_v1) {
         if (!(phases & 2)) return B200TIMG_OK;
         return launch_sixel_emit(ctx, w, h, n_frames, W, d_out, out_cap, d_offsets);
     }
     if (phases & 1) {
-        B2_KERNEL(ctx, "sixel_emit_kernel");
-        sixel_emit_kernel<<<egrid, ET, emit_smem, ctx->stream>>>(G, W);
-        B2_LAUNCH_CHECK(ctx);
         B2_KERNEL(ctx, "sixel_layout_kernel");
         sixel_layout_kernel<<<n_frames, 256, 0, ctx->stream>>>(w, h, W);
         B2_LAUNCH_CHECK(ctx);
@@ -931,9 +961,17 @@ int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_fra
     }
     if (!(phases & 2)) return B200TIMG_OK;
     B2_KERNEL(ctx, "sixel_compact_kernel");
-    sixel_compact_kernel<<<egrid, 256, 0, ctx->stream>>>(w, h, W, d_offsets, d_out, (unsigned long long)out_cap);
+    sixel_compact_kernel<<<dim3(W.nbands, n_frames), 256, 0, ctx->stream>>>(w, h, W, d_offsets, d_out, (unsigned long long)out_cap);
     B2_LAUNCH_CHECK(ctx);
     return B200TIMG_OK;
+}
+
+// phases: 1 = everything up to and including the frame offsets (sizes known, nothing written),
+//         2 = write the bytes.  3 = both, back to back without a host round trip.
+int launch_sixel(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int n_frames, char *d_out,
+                 size_t out_cap, uint64_t *d_offsets, int phases) {
+    if (phases & 1) B2_TRY(launch_sixel_front(ctx, d_fb, w, h, n_frames, 0, n_frames, true));
+    return launch_sixel_back(ctx, w, h, n_frames, d_out, out_cap, d_offsets, phases);
 }
 
 // Introspection for tests: palette, colour counts and index plane of frame 0 of the last encode.

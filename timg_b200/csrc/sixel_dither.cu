@@ -221,14 +221,17 @@ size_t sixel_dither_workspace(int w, int h, int n_frames, size_t *o_bnd, size_t 
     return off;
 }
 
-int launch_sixel_dither(b200timg_ctx *ctx, const uint32_t *fb, int w, int h, int n_frames, const SixelWork &W, void *d_bnd, void *d_prog) {
+// n_frames: frames of this launch (fb, W, d_bnd and d_prog already point at its first frame); n_total: frames of the
+// whole batch this launch is a slice of -- the "split a frame over several CTAs" decision looks at the batch, so a
+// slice that shares the GPU with another slice does not spread itself over every SM.
+int launch_sixel_dither(b200timg_ctx *ctx, const uint32_t *fb, int w, int h, int n_frames, int n_total, const SixelWork &W, void *d_bnd, void *d_prog) {
     Dither2Geom G;
     G.w = w; G.h = h; G.nb32 = (h + 31) / 32;
     // CTAs per frame: 1 when the batch fills the GPU, more (up to one round of bands per CTA) for small batches.
     // All CTAs of a launch must be resident together when a frame is split (bands wait for the band above).
     int per_frame = 1;
-    if (n_frames < ctx->sm_count) {
-        per_frame = std::max(1, std::min(ctx->sm_count / n_frames, (G.nb32 + 7) / 8));
+    if (n_total < ctx->sm_count) {
+        per_frame = std::max(1, std::min(ctx->sm_count / n_total, (G.nb32 + 7) / 8));
         if (const char *e = getenv("B200TIMG_DITHER_SPLIT")) per_frame = std::max(1, std::min(atoi(e), G.nb32));
         if ((long long)per_frame * n_frames > ctx->sm_count) per_frame = std::max(1, ctx->sm_count / n_frames);
     }
