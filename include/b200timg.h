@@ -25,6 +25,8 @@
  *
  * Threading: a ctx is thread-compatible (one caller at a time per ctx), like the
  * reference's canvases (src/unicode-block-canvas.h:70-79 are plain members).
+ * Current device: every entry point that takes a ctx makes the ctx's device the calling thread's current CUDA
+ * device (cudaSetDevice) and leaves it so; hosts that juggle several devices in one thread re-select theirs.
  */
 #ifndef B200TIMG_H
 #define B200TIMG_H
@@ -144,7 +146,9 @@ int b200timg_blocks_encode(b200timg_ctx *ctx, const uint8_t *fb, int w, int h,
                            const uint8_t *prev_fb, int flags, int x_indent_cells,
                            char *out, size_t cap, size_t *size);
 
-/* Worst-case encoded size of one sixel frame of w x h (h a multiple of 6). */
+/* Worst-case encoded size of one sixel frame of w x h (h a multiple of 6).
+ * Size limits of the sixel path (the reference has none; both are far beyond any terminal): w <= 99999 and
+ * h <= 65536.  Frames up to 4095 px wide take the fast emit kernel, wider ones a column-tiled one. */
 size_t b200timg_sixel_bound(int w, int h);
 
 /* What libsixel does inside SixelCanvas::Send (src/sixel-canvas.cc:134-148):
@@ -184,7 +188,13 @@ typedef struct {
 } b200timg_batch;
 
 /* Device-resident variants: d_src, d_out, d_offsets are DEVICE pointers; nothing crosses
- * PCIe.  The call is asynchronous on the ctx stream except where it must read a size. */
+ * PCIe.  The call is asynchronous on the ctx stream (no size is read back).
+ * OUTPUT CAPACITY CONTRACT: the call cannot fail with B200TIMG_ENOSPC because it never learns the sizes on the
+ * host.  d_offsets is always complete and exact (d_offsets[n_frames] = the bytes the batch needs); a frame whose
+ * end would lie beyond out_cap is NOT written (nothing is ever written out of bounds, earlier frames are intact).
+ * The caller therefore either passes out_cap >= n_frames * b200timg_{blocks,sixel}_bound(out_w, padded out_h)
+ * (cannot overflow) or compares d_offsets[n_frames] with out_cap when it reads the offsets, and repeats the call
+ * with a larger buffer if it is greater -- exactly what the host variants do internally. */
 int b200timg_blocks_batch_dev(b200timg_ctx *ctx, const b200timg_batch *b,
                               const uint8_t *d_src, char *d_out, size_t out_cap,
                               uint64_t *d_offsets);

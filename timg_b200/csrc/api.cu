@@ -67,6 +67,8 @@ void b200timg_ctx_destroy(b200timg_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto &r : ctx->prof) { cudaEventDestroy(r.begin); cudaEventDestroy(r.end); }
+    ctx->prof.clear();
     b200timg_gather_shutdown(ctx);
     ctx->gather_status.release();
     ctx->in_stage.release(); ctx->fb_scaled.release(); ctx->prev_stage.release();
@@ -93,7 +95,7 @@ uint64_t b200timg_kernel_launches(const b200timg_ctx *ctx) { return ctx ? ctx->l
 
 // ---- per-kernel timing --------------------------------------------------------------------
 int b200timg_profile(b200timg_ctx *ctx, int enable) {
-    if (!ctx) return B200TIMG_EINVAL;
+    if (const int rc = check_ctx(ctx)) return rc;
     cudaStreamSynchronize(ctx->stream);
     for (auto &r : ctx->prof) { cudaEventDestroy(r.begin); cudaEventDestroy(r.end); }
     ctx->prof.clear();
