@@ -883,10 +883,8 @@ static int sixel_plan(b200timg_ctx *ctx, int w, int h, int n_frames, bool reserv
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + DW_MAX * DWARP_SMEM));
-        const size_t t_words = W.ent_cap > 16384 ? (size_t)W.ent_cap : 16384;
-        const size_t smem_tables = sizeof(uint32_t) * (t_words + (size_t)W.ent_cap);
-        if (smem_tables <= 200 * 1024)
-            B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        // unconditionally: which variant a frame takes depends on ITS size, not on the first frame this context saw
+        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ctx->sixel_attrs_set = true;
     }
     return B200TIMG_OK;
