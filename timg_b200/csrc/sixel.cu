@@ -825,6 +825,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct SixelPlan {
     SixelWork W;
     bool emit_v1, dither_v1;
+    int emit_mode;                            // 1: v1 (scratch arena + compaction), 2: emit2, 3: emit3 (default)
     EmitGeom G;
     size_t emit_smem, o_d2_bnd, o_d2_prog;
     long long npix;
@@ -854,9 +855,19 @@ static int sixel_plan(b200timg_ctx *ctx, int w, int h, int n_frames, bool reserv
     // worst case of one band: <= 6 entries per column, <= 7 bytes each ("!nnnn?" + char), "$#ccc" per colour
     W.band_cap = align_up((size_t)w * 42 + 256 * 5 + 16, 256);
     const size_t o_scr = off;
-    // two emitters: v1 (per-band sizes into a scratch arena + compaction kernel; <= 4095 px wide) and the single-pass v2
-    // (sixel_emit.cu: any width, no arena).  v2 is used where v1 cannot go and when B200TIMG_EMIT_V2 is set.
-    S->emit_v1 = !getenv("B200TIMG_EMIT_V2") && w <= 4095 && sizeof(uint32_t) * (size_t)6 * w <= (size_t)(227 - 36) * 1024;
+    // three emitters (B200TIMG_EMIT=1|2|3): emit3 (sixel_emit.cu; the default: v1's sort, entry-parallel formatting, bytes
+    // placed by a decoupled look-back -- any width, no arena), v1 (per-band sizes into a scratch arena + compaction
+    // kernel; <= 4095 px wide; kept for A/B runs) and emit2 (the first single-pass emitter; kept for A/B runs).
+    {
+        const bool v1_fits = w <= 4095 && sizeof(uint32_t) * (size_t)6 * w <= (size_t)(227 - 36) * 1024;
+        int mode = 3;
+        if (getenv("B200TIMG_EMIT_V2")) mode = 2;
+        if (const char *e = getenv("B200TIMG_EMIT")) mode = atoi(e);
+        if (mode == 1 && !v1_fits) mode = 3;
+        if (mode < 1 || mode > 3) mode = 3;
+        S->emit_mode = mode;
+        S->emit_v1 = mode == 1;
+    }
     if (S->emit_v1) off += W.band_cap * W.nbands * n_frames;
     S->dither_v1 = getenv("B200TIMG_DITHER_V1") != nullptr;      // round-1 ditherer, kept for A/B runs
     size_t d_bnd, d_prog;
@@ -947,7 +958,8 @@ int launch_sixel_back(b200timg_ctx *ctx, int w, int h, int n_frames, char *d_out
     const SixelWork &W = S.W;
     if (!S.emit_v1) {
         if (!(phases & 2)) return B200TIMG_OK;
-        return launch_sixel_emit(ctx, w, h, n_frames, W, d_out, out_cap, d_offsets);
+        if (S.emit_mode == 2) return launch_sixel_emit(ctx, w, h, n_frames, W, d_out, out_cap, d_offsets);
+        return launch_sixel_emit3(ctx, w, h, n_frames, W, d_out, out_cap, d_offsets);
     }
     if (phases & 1) {
         B2_KERNEL(ctx, "sixel_layout_kernel");
