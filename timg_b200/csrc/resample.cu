@@ -16,7 +16,44 @@
 #include "common.cuh"
 #include "resample_tables.h"
 
+#ifndef CUSIM
+#include <cuda.h>            // CUtensorMap: types only -- the encoder comes from the runtime's driver entry point, nothing links libcuda
+#else
+struct alignas(64) CUtensorMap { unsigned long long opaque[16]; };
+#define __grid_constant__
+#endif
+
 namespace b200timg {
+
+// ---- TMA (cp.async.bulk.tensor) staging of a source window: one thread issues the copy of a [rows][cols] box of the
+// [frames][ih][iw] u32 tensor into shared memory, the hardware fills cells outside the image with zeros and signals an
+// mbarrier with the byte count.  SASS: UTMALDG + SYNCS.
+#ifndef CUSIM
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+#endif
 
 struct ResampleParams {
     int iw, ih, ow, oh, out_frame_rows, n_frames;
@@ -914,6 +951,29 @@ resample_copy_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out
     }
 }
 
+// scale 1 in both axes and identity tap tables (the C5 shape: frames shown unscaled): 16-byte copies, 4 pixels per thread,
+// compose fused.  grid = (quads of a frame, frames).
+__global__ void __launch_bounds__(256)
+resample_copy4_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P) {
+    const int qpr = P.ow >> 2, nq = qpr * P.oh, f = blockIdx.y;
+    const uint4 *src = reinterpret_cast<const uint4 *>(in + (long long)f * P.iw * P.ih);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + (long long)f * P.out_frame_rows * P.ow);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        uint4 v = __ldcs(src + q);                                       // read once
+        if (P.bgra) {
+            v.x = (v.x & 0xff00ff00u) | ((v.x & 0xff) << 16) | ((v.x >> 16) & 0xff);
+            v.y = (v.y & 0xff00ff00u) | ((v.y & 0xff) << 16) | ((v.y >> 16) & 0xff);
+            v.z = (v.z & 0xff00ff00u) | ((v.z & 0xff) << 16) | ((v.z >> 16) & 0xff);
+            v.w = (v.w & 0xff00ff00u) | ((v.w & 0xff) << 16) | ((v.w >> 16) & 0xff);
+        }
+        if (P.cs.active && (v.x & v.y & v.z & v.w) < 0xff000000u) {      // some pixel of the group is not opaque
+            const int oy = q / qpr, ox = (q - oy * qpr) << 2;
+            v.x = compose_at(P.cs, v.x, ox, oy); v.y = compose_at(P.cs, v.y, ox + 1, oy);
+            v.z = compose_at(P.cs, v.z, ox + 2, oy); v.w = compose_at(P.cs, v.w, ox + 3, oy);
+        }
+        dst[q] = v;
+    }
+}
 
 // ---- v3: opaque tiles, vertical pass first, <= 8 taps per axis ------------------------------
 // What limits the planar kernel above is shared-memory bandwidth and issue slots spent outside the tap
@@ -963,13 +1023,15 @@ template <bool EXACT> __device__ __forceinline__ float byte_val(uint32_t p, uint
     return EXACT ? fmul(v, 1.0f / 255.0f) : v;
 }
 
-struct V3Geom { int nix, niy, sp, tp; unsigned grp_magic; const int32_t *tile_ix0, *tile_iy0; uint32_t *fallback; };   // grp_magic: floor(2^32/(sp/4))+1
+struct V3Geom { int nix, niy, sp, tp; unsigned grp_magic; const int32_t *tile_ix0, *tile_iy0; uint32_t *fallback; int use_tma; };   // grp_magic: floor(2^32/(sp/4))+1
 constexpr int V3_TW = 64, V3_TH = 32, V3_NT = 256, V3_MINB = 2;
 
 template <int HC, int VC, bool EXACT>
 __global__ void __launch_bounds__(V3_NT, V3_MINB)
-resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, V3Geom G) {
-    extern __shared__ float4 s_px[];
+resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, ResampleParams P, V3Geom G,
+                   const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float4 s_px[];
+    __shared__ __align__(8) unsigned long long s_mbar;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, f = blockIdx.z;
     const int ox0 = blockIdx.x * V3_TW, oy0 = blockIdx.y * V3_TH;
     const int ix0 = G.tile_ix0[blockIdx.x], iy0 = G.tile_iy0[blockIdx.y];
@@ -982,6 +1044,16 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     int *s_hfirst = reinterpret_cast<int *>(s_vc + V3_TH * 8);               // [V3_TW]
     int *s_vfirst = s_hfirst + V3_TW;                                        // [V3_TH]
     uint32_t *O = S;                                                         // [V3_TH][V3_TW + 1] once S is dead
+#ifndef CUSIM
+    if (G.use_tma) {                                                         // the window is on its way while the tap tables are set up
+        if (tid == 0) mbar_init(&s_mbar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&s_mbar, (uint32_t)(niy * sp) * 4u);
+            tma_load_3d(S, &tmap, &s_mbar, ix0, iy0, f);
+        }
+    }
+#endif
     if (tid < V3_TW) {
         const int ox = ox0 + tid;
         const bool ok = ox < P.ow;
@@ -999,6 +1071,24 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     const uint32_t *src = in + (long long)f * P.iw * P.ih;
     const int ngrp = sp >> 2, n_stage = niy * ngrp;
     bool ok255 = true;
+#ifndef CUSIM
+    if (G.use_tma) {
+        mbar_wait(&s_mbar, 0);                                               // the window has landed (zero-filled outside the image)
+        if (iy0 + niy <= P.ih && ix0 + sp <= P.iw) {                         // interior tile: every cell is a pixel
+            uint32_t m = 0xffffffffu;
+            for (int u = tid; u < n_stage; u += V3_NT) { const uint4 raw = reinterpret_cast<const uint4 *>(S)[u]; m &= raw.x & raw.y & raw.z & raw.w; }
+            ok255 = m >= 0xff000000u;
+        } else {
+            for (int u = tid; u < n_stage; u += V3_NT) {
+                const int ly = (int)__umulhi((unsigned)u, G.grp_magic), g = u - ly * ngrp;
+                if (iy0 + ly < P.ih && ix0 + 4 * g < P.iw) {                 // iw % 4 == 0 on this path: a group is inside or outside as a whole
+                    const uint4 raw = *reinterpret_cast<const uint4 *>(S + ly * sp + 4 * g);
+                    ok255 = ok255 && ((raw.x & raw.y & raw.z & raw.w) >= 0xff000000u);
+                }
+            }
+        }
+    } else
+#endif
     for (int u = tid; u < n_stage; u += V3_NT) {
         const int ly = (int)__umulhi((unsigned)u, G.grp_magic), g = u - ly * ngrp;
         const int y = iy0 + ly, x = ix0 + 4 * g;
@@ -1151,7 +1241,35 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     }
 }
 
-typedef void (*V3Fn)(const uint32_t *, uint32_t *, ResampleParams, V3Geom);
+// Tensor map of a batch of source frames for the v3 kernel's window: u32 elements, dims (iw, ih, frames), box (cols, rows, 1),
+// no swizzle, zero fill outside.  False when the geometry does not meet TMA's alignment rules (the kernel then stages
+// with plain 16-byte loads) or when B200TIMG_TMA=0.
+static bool v3_tensor_map(CUtensorMap *map, const uint32_t *src, int iw, int ih, int n_frames, int box_cols, int box_rows) {
+#ifdef CUSIM
+    return false;
+#else
+    if (const char *e = getenv("B200TIMG_TMA")) if (atoi(e) == 0) return false;
+    if ((iw & 3) || (reinterpret_cast<uintptr_t>(src) & 15) || box_cols > 256 || box_rows > 256 || (box_cols & 3)) return false;
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    if (!encode) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)iw, (cuuint64_t)ih, (cuuint64_t)n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)iw * 4, (cuuint64_t)iw * ih * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint32_t *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+#endif
+}
+
+typedef void (*V3Fn)(const uint32_t *, uint32_t *, ResampleParams, V3Geom, const CUtensorMap);
 template <int HC, bool EXACT>
 static V3Fn v3_v(int vc) {
     switch (vc) {
@@ -1242,7 +1360,16 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
     P.v_coeff = reinterpret_cast<const float *>(t + o_vk);
     const uint32_t *in = reinterpret_cast<const uint32_t *>(d_in);
     uint32_t *out = reinterpret_cast<uint32_t *>(d_out);
-    if (pl->copy_only) {
+    bool identity = pl->copy_only && iw == ow && ih == oh && (ow & 3) == 0 && n_frames <= 65535 && (long long)ow * oh < (1ll << 31) &&
+                    ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
+    for (int x = 0; identity && x < ow; ++x) identity = pl->h.first[x] == x;
+    for (int y = 0; identity && y < oh; ++y) identity = pl->v.first[y] == y;
+    if (identity) {
+        const int nq = (ow >> 2) * oh;
+        const int bx = std::max(1, std::min((nq + 255) / 256, std::max(1, ctx->sm_count * 8 / std::max(1, std::min(n_frames, ctx->sm_count * 8)))));
+        B2_KERNEL(ctx, "resample_copy_kernel");
+        resample_copy4_kernel<<<dim3((unsigned)bx, (unsigned)n_frames), 256, 0, ctx->stream>>>(in, out, P);
+    } else if (pl->copy_only) {
         long long blocks = ((long long)ow * oh * n_frames + 255) / 256;
         if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
         B2_KERNEL(ctx, "resample_copy_kernel");
@@ -1297,11 +1424,14 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
                     B2_CUDA(ctx, ctx->scale_list.reserve(sizeof(uint32_t) * list_words * (size_t)ctx->part_slots));
                     uint32_t *d_list = ctx->scale_list.as<uint32_t>() + list_words * (size_t)ctx->part_slot;
                     B2_CUDA(ctx, cudaMemsetAsync(d_list, 0, sizeof(uint32_t), ctx->stream));
-                    V3Geom VG{nix3, niy, sp3, tp3, (unsigned)(0x100000000ull / (unsigned)(sp3 / 4)) + 1u, d_t + ntx + nty, d_t + ntx, d_list};
+                    V3Geom VG{nix3, niy, sp3, tp3, (unsigned)(0x100000000ull / (unsigned)(sp3 / 4)) + 1u, d_t + ntx + nty, d_t + ntx, d_list, 0};
+                    CUtensorMap tmap;
+                    memset(&tmap, 0, sizeof tmap);
+                    VG.use_tma = v3_tensor_map(&tmap, in, iw, ih, n_frames, sp3, niy) ? 1 : 0;
                     V3Fn fn = fast ? v3_h<false>(hc, vc) : v3_h<true>(hc, vc);
                     B2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
                     B2_KERNEL(ctx, fast ? "resample_v3_fast_kernel" : "resample_v3_exact_kernel");
-                    fn<<<dim3(ntx3, nty, n_frames), V3_NT, v3smem, ctx->stream>>>(in, out, P, VG);
+                    fn<<<dim3(ntx3, nty, n_frames), V3_NT, v3smem, ctx->stream>>>(in, out, P, VG, tmap);
                     B2_LAUNCH_CHECK(ctx);
                     PlanarListFn lf = planar_list_h(hc, vc);              // tiles with transparency (none for photos / video)
                     B2_CUDA(ctx, cudaFuncSetAttribute(lf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));

@@ -56,7 +56,7 @@ template <int K> __device__ __forceinline__ uint32_t tap_b(const TapW &t) {
 }
 __device__ __forceinline__ uint32_t add_clamp(uint32_t v, uint32_t t) { return __viaddmin_s16x2_relu(v, t, 0x00ff00ffu); }
 
-struct Dither2Geom { int w, h, nb32, bands_per_cta, nwarps; };
+struct Dither2Geom { int w, h, nb32, bands_per_cta, nwarps; unsigned spin_ns; };   // spin_ns: pause between two polls of the band above
 
 __global__ void __launch_bounds__(D2_WMAX * 32)
 sixel_dither2_kernel(const uint32_t *__restrict__ fb, Dither2Geom G, SixelWork W, uint4 *__restrict__ bnd_all, int *__restrict__ gprog_all) {
@@ -126,8 +126,8 @@ sixel_dither2_kernel(const uint32_t *__restrict__ fb, Dither2Geom G, SixelWork W
             if (band > 0) {                                      // stay behind the band above's last row
                 const int need = min(w, t0 + D2_CH + 1);
                 if (lane == 0) {
-                    if (prev_remote) { while (gprog[band - 1] < need) __nanosleep(64); __threadfence(); }
-                    else { while (s_progress[lb - 1] < need) __nanosleep(32); __threadfence_block(); }
+                    if (prev_remote) { while (gprog[band - 1] < need) __nanosleep(G.spin_ns); __threadfence(); }
+                    else { while (s_progress[lb - 1] < need) __nanosleep(G.spin_ns); __threadfence_block(); }
                 }
                 __syncwarp();
                 const int bx = t0 + 1 + lane;                    // lane 0 consumes column t+1 at step t
@@ -227,6 +227,10 @@ size_t sixel_dither_workspace(int w, int h, int n_frames, size_t *o_bnd, size_t 
 int launch_sixel_dither(b200timg_ctx *ctx, const uint32_t *fb, int w, int h, int n_frames, int n_total, const SixelWork &W, void *d_bnd, void *d_prog) {
     Dither2Geom G;
     G.w = w; G.h = h; G.nb32 = (h + 31) / 32;
+    // A chunk of 16 columns x 32 rows takes a warp several microseconds; polling the band above every 32 ns spent 13.6 % of
+    // the kernel's issue slots in the wait loop (profiles/r2_lines_sixel_dither2.txt), slots the producing warps need.
+    G.spin_ns = 256;
+    if (const char *e = getenv("B200TIMG_DITHER_SPIN")) G.spin_ns = (unsigned)std::max(0, std::min(atoi(e), 100000));
     // CTAs per frame: 1 when the batch fills the GPU, more (up to one round of bands per CTA) for small batches.
     // All CTAs of a launch must be resident together when a frame is split (bands wait for the band above).
     int per_frame = 1;

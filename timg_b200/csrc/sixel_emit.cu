@@ -331,7 +331,13 @@ constexpr uint32_t E3_CHUNK_MAX = 32 * 19;                      // "$#255" + "!9
 constexpr uint32_t E3_WIN = E3_TAB_WORDS * 4 - 640;             // chunks STARTING below this offset of a window are formatted into it
 static_assert(E3_WIN + E3_CHUNK_MAX <= E3_TAB_WORDS * 4, "a window must hold its last chunk");
 
-struct Emit3Geom { int w, h, nbands, ntiles, tw, cpw, ent_cap; unsigned n_cta; };
+struct Emit3Geom { int w, h, nbands, ntiles, tw, cpw, ent_cap; unsigned n_cta; int dbg; };   // dbg: timing experiments (B200TIMG_E3DBG), output invalid when set
+#ifdef CUSIM
+unsigned long long g_dbg[8];
+#define DBG(i) do { if (lane == 0) ++g_dbg[i]; } while (0)
+#else
+#define DBG(i)
+#endif
 
 // decimal digits of v (< 100000), most significant first, as a little-endian byte string of nd bytes
 __device__ __forceinline__ unsigned long long dec5(uint32_t v, uint32_t nd) {
@@ -472,6 +478,7 @@ sixel_emit3_kernel(Emit3Geom G, SixelWork W, uint64_t *__restrict__ offsets, cha
     const bool lead_dollar = tile > 0;
     {
         uint32_t local = 0;
+        for (int ck = c_lo; ck < c_hi; ++ck) DBG(2);
         for (int ck = c_lo; ck < c_hi; ++ck) local += run_step(s_sorted, ck * 32, lane, n, (uint32_t)x0, lead_dollar).size;
         local = __reduce_add_sync(0xffffffffu, local);
         if (lane == 0) s_wtot[wid] = local;
@@ -484,6 +491,9 @@ sixel_emit3_kernel(Emit3Geom G, SixelWork W, uint64_t *__restrict__ offsets, cha
     const uint32_t pre = (tile == 0 && band > 0) ? 1u : 0u;            // '-' : next band
     const unsigned long long agg = (unsigned long long)hdr_len + pre + band_total + (last_cta ? 2u : 0u);
     // ---- look-back (warp 0) while the other warps already format
+    if (wid == 0 && (G.dbg & 1)) {                                      // timing experiment: no look-back, fixed slots
+        if (lane == 0) s_excl = (unsigned long long)vid * 20000ull;
+    } else
     if (wid == 0) {
         const unsigned long long VMASK = (1ull << 62) - 1ull;
         volatile unsigned long long *desc = W.desc;
@@ -510,10 +520,13 @@ sixel_emit3_kernel(Emit3Geom G, SixelWork W, uint64_t *__restrict__ offsets, cha
     bool ovf = false;
     int ck = c_lo;
     for (uint32_t win0 = 0;;) {
+        DBG(0);
         while (ck < c_hi && run_off < win0 + E3_WIN) {
+            DBG(1);
             const RunStep r = run_step(s_sorted, ck * 32, lane, n, (uint32_t)x0, lead_dollar);
             const uint32_t incl = warp_incl_scan(r.size, lane);
             uint8_t *p = wbuf + (run_off - win0) + (incl - r.size);
+            if (G.dbg & 2) { run_off += __shfl_sync(0xffffffffu, incl, 31); ++ck; continue; }   // timing experiment: no formatting
             const bool intro = r.head && r.first;
             if (__any_sync(0xffffffffu, intro)) {                       // "$#ccc"
                 uint32_t len = 0;
@@ -601,6 +614,8 @@ int launch_sixel_emit3(b200timg_ctx *ctx, int w, int h, int n_frames, const Sixe
     const unsigned long long n_cta = (unsigned long long)n_frames * G.nbands * G.ntiles;
     if (n_cta > 0x7fffffffull) return ctx->fail(B200TIMG_EINVAL, "sixel: too many bands for one launch");
     G.n_cta = (unsigned)n_cta;
+    G.dbg = 0;
+    if (const char *e = getenv("B200TIMG_E3DBG")) G.dbg = atoi(e);
     const size_t smem = sizeof(uint32_t) * (size_t)G.ent_cap;
     B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // descriptors + ticket + status are contiguous: one memset
@@ -611,6 +626,9 @@ int launch_sixel_emit3(b200timg_ctx *ctx, int w, int h, int n_frames, const Sixe
     B2_KERNEL(ctx, "sixel_emit3_kernel");
     sixel_emit3_kernel<<<G.n_cta, E3T, smem, ctx->stream>>>(G, W, d_offsets, d_out, (unsigned long long)out_cap);
     B2_LAUNCH_CHECK(ctx);
+#ifdef CUSIM
+    if (getenv("B200TIMG_DBG")) fprintf(stderr, "emit3 dbg: ctas %u window-iterations(warps) %llu chunksB %llu chunksA %llu\n", G.n_cta, g_dbg[0], g_dbg[1], g_dbg[2]);
+#endif
     return B200TIMG_OK;
 }
 
