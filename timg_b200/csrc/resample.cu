@@ -1023,6 +1023,23 @@ template <bool EXACT> __device__ __forceinline__ float byte_val(uint32_t p, uint
     return EXACT ? fmul(v, 1.0f / 255.0f) : v;
 }
 
+// two bytes -> a float pair.  FAST: two PRMTs into the mantissa of 2^23 and ONE packed subtraction.
+template <bool EXACT> __device__ __forceinline__ F2 byte_pair(uint32_t pa, uint32_t sa, uint32_t pb, uint32_t sb) {
+    if (EXACT) return F2{byte_val<true>(pa, sa), byte_val<true>(pb, sb)};
+    return f2_add(F2{__uint_as_float(__byte_perm(pa, 0x4B000000u, sa)), __uint_as_float(__byte_perm(pb, 0x4B000000u, sb))},
+                  F2{-8388608.0f, -8388608.0f});
+}
+// trunc(clamp(v + 0.5, 0, 255)): the float -> u8 conversion saturates by itself
+__device__ __forceinline__ uint32_t sat_u8(float v) {
+#ifdef CUSIM
+    return __float2uint_rz(fminf(fmaxf(v + 0.5f, 0.0f), 255.0f));
+#else
+    uint32_t r;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(v + 0.5f));
+    return r;
+#endif
+}
+
 struct V3Geom { int nix, niy, sp, tp; unsigned grp_magic; const int32_t *tile_ix0, *tile_iy0; uint32_t *fallback; int use_tma; };   // grp_magic: floor(2^32/(sp/4))+1
 constexpr int V3_TW = 64, V3_TH = 32, V3_NT = 256, V3_MINB = 2;
 
@@ -1071,13 +1088,12 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     const uint32_t *src = in + (long long)f * P.iw * P.ih;
     const int ngrp = sp >> 2, n_stage = niy * ngrp;
     bool ok255 = true;
+    bool fold = false;                 // interior TMA tile: every cell is a pixel, the opacity test rides on the vertical pass's loads
 #ifndef CUSIM
     if (G.use_tma) {
         mbar_wait(&s_mbar, 0);                                               // the window has landed (zero-filled outside the image)
-        if (iy0 + niy <= P.ih && ix0 + sp <= P.iw) {                         // interior tile: every cell is a pixel
-            uint32_t m = 0xffffffffu;
-            for (int u = tid; u < n_stage; u += V3_NT) { const uint4 raw = reinterpret_cast<const uint4 *>(S)[u]; m &= raw.x & raw.y & raw.z & raw.w; }
-            ok255 = m >= 0xff000000u;
+        if (iy0 + niy <= P.ih && ix0 + sp <= P.iw) {
+            fold = true;
         } else {
             for (int u = tid; u < n_stage; u += V3_NT) {
                 const int ly = (int)__umulhi((unsigned)u, G.grp_magic), g = u - ly * ngrp;
@@ -1114,6 +1130,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     // last tap arrives -- its taps are then exactly the window, oldest first.  Loads and byte->float conversions per
     // intermediate pixel drop from VC to ~1.4 (input rows per output row, plus the window warm-up of each group).
     const int ncp = sp >> 1;
+    uint32_t amask = 0xffffffffu;                                            // AND of every pixel this thread reads
     {
         const int j0 = (wid >> 1) * 8, j1 = j0 + 8;
         const int f0 = s_vfirst[j0], rend = s_vfirst[j1 - 1] + VC;            // input rows [f0, rend) of the window
@@ -1128,9 +1145,10 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                     const int r = r0 + sl;
                     if (r < rend) {
                         const uint2 pp = *reinterpret_cast<const uint2 *>(scol + r * sp);
-                        w0[sl] = F2{byte_val<EXACT>(pp.x, sel_r), byte_val<EXACT>(pp.x, sel_g)};
-                        w1[sl] = F2{byte_val<EXACT>(pp.y, sel_r), byte_val<EXACT>(pp.y, sel_g)};
-                        wb[sl] = F2{byte_val<EXACT>(pp.x, sel_b), byte_val<EXACT>(pp.y, sel_b)};
+                        amask &= pp.x & pp.y;
+                        w0[sl] = byte_pair<EXACT>(pp.x, sel_r, pp.x, sel_g);
+                        w1[sl] = byte_pair<EXACT>(pp.y, sel_r, pp.y, sel_g);
+                        wb[sl] = byte_pair<EXACT>(pp.x, sel_b, pp.y, sel_b);
                         while (j < j1 && ej == r) {                           // uniform: every thread walks the same rows
                             const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + j * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + j * 8 + 4);
                             const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -1154,7 +1172,14 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
             }
         }
     }
-    __syncthreads();
+    if (!__syncthreads_and(!fold || amask >= 0xff000000u)) {      // (interior TMA tiles) a pixel that was read is not opaque
+        if (tid == 0) {
+            const uint32_t k = atomicAdd(G.fallback, 1u);
+            uint32_t *e = G.fallback + 1 + 3 * k;
+            e[0] = blockIdx.x; e[1] = blockIdx.y; e[2] = blockIdx.z;
+        }
+        return;
+    }
     // ---- horizontal, streaming the same way along x: lane = output row, a warp owns 8 consecutive output columns
     // and walks the intermediate columns they need once (window of HC columns in registers).  Pixels go straight
     // into the transpose buffer O (it aliases S, which is dead now).
@@ -1216,9 +1241,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                             v[0] = c2.x; v[1] = c2.y; v[2] = cb; v[3] = al; v[4] = c2.x; v[5] = c2.y; v[6] = cb;
                             px = compose_at(P.cs, encode_px(v), ox0 + tx, oy0 + lane);
                         } else {
-                            const uint32_t r8 = __float2uint_rz(fminf(fmaxf(c2.x + 0.5f, 0.0f), 255.0f));
-                            const uint32_t g8 = __float2uint_rz(fminf(fmaxf(c2.y + 0.5f, 0.0f), 255.0f));
-                            const uint32_t b8 = __float2uint_rz(fminf(fmaxf(cb + 0.5f, 0.0f), 255.0f));
+                            const uint32_t r8 = sat_u8(c2.x), g8 = sat_u8(c2.y), b8 = sat_u8(cb);
                             px = pack_rgba(r8, g8, b8, 0xffu);                    // opaque in, opaque out: nothing to compose
                         }
                         O[lane * (V3_TW + 1) + tx] = px;

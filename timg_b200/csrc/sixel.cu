@@ -855,16 +855,16 @@ static int sixel_plan(b200timg_ctx *ctx, int w, int h, int n_frames, bool reserv
     // worst case of one band: <= 6 entries per column, <= 7 bytes each ("!nnnn?" + char), "$#ccc" per colour
     W.band_cap = align_up((size_t)w * 42 + 256 * 5 + 16, 256);
     const size_t o_scr = off;
-    // three emitters (B200TIMG_EMIT=1|2|3): emit3 (sixel_emit.cu; the default: v1's sort, entry-parallel formatting, bytes
-    // placed by a decoupled look-back -- any width, no arena), v1 (per-band sizes into a scratch arena + compaction
-    // kernel; <= 4095 px wide; kept for A/B runs) and emit2 (the first single-pass emitter; kept for A/B runs).
+    // three emitters (B200TIMG_EMIT=1|2|3): v1 (the default up to 4095 px: per-band sizes into a scratch arena + compaction
+    // kernel), emit2 (sixel_emit.cu: single pass, any width -- what wider frames get) and emit3 (v1's sort + entry-parallel
+    // formatting + look-back placement; measured SLOWER than v1, profiles/r2_notes.md: 9.2 ms without and 63 ms with the
+    // look-back against v1's 5.2 + 0.36 ms per 148 C2 frames; kept for A/B runs only).
     {
         const bool v1_fits = w <= 4095 && sizeof(uint32_t) * (size_t)6 * w <= (size_t)(227 - 36) * 1024;
-        int mode = 3;
+        int mode = v1_fits ? 1 : 2;
         if (getenv("B200TIMG_EMIT_V2")) mode = 2;
         if (const char *e = getenv("B200TIMG_EMIT")) mode = atoi(e);
-        if (mode == 1 && !v1_fits) mode = 3;
-        if (mode < 1 || mode > 3) mode = 3;
+        if (mode < 1 || mode > 3 || (mode == 1 && !v1_fits)) mode = 2;
         S->emit_mode = mode;
         S->emit_v1 = mode == 1;
     }

@@ -316,7 +316,8 @@ sixel_header_kernel(int w, int h, SixelWork W) {
 
 
 // ---------------------------------------------------------------------------------------------------------
-// emit3 (the default emitter).  Same grammar and the same bytes as the two-pass v1 emitter of sixel.cu, built from
+// emit3 (EXPERIMENT, B200TIMG_EMIT=3; not the default: it measured slower than v1, see profiles/r2_notes.md).  Same
+// grammar and the same bytes as the two-pass v1 emitter of sixel.cu, built from
 //   * v1's per-band counting sort (warps own column ranges, per-warp count / mask tables),
 //   * an ENTRY-PARALLEL sizing and formatting stage: a warp takes 32 consecutive sorted entries at a time; run heads,
 //     run lengths (next head in the ballot), gaps and byte sizes are lane-local arithmetic on the neighbouring
