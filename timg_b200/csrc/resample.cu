@@ -1058,8 +1058,10 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     float *TB = reinterpret_cast<float *>(TRG + V3_TH * tp);                 // [V3_TH][tp]
     float *s_hc = TB + V3_TH * tp + ((4 - ((V3_TH * tp) & 3)) & 3);         // [V3_TW][8], 16-byte aligned (tp odd, V3_TH * tp * 12 % 16 handled here)
     float *s_vc = s_hc + V3_TW * 8;                                          // [V3_TH][8]
-    int *s_hfirst = reinterpret_cast<int *>(s_vc + V3_TH * 8);               // [V3_TW]
-    int *s_vfirst = s_hfirst + V3_TW;                                        // [V3_TH]
+    // completion index of every output column / row of the tile: the window column / row at which its LAST tap arrives
+    // (first + taps - 1), and a -1 behind the last entry so the walks below stop without a bound check
+    int *s_hlast = reinterpret_cast<int *>(s_vc + V3_TH * 8);                // [V3_TW + 1]
+    int *s_vlast = s_hlast + V3_TW + 1;                                      // [V3_TH + 1]
     uint32_t *O = S;                                                         // [V3_TH][V3_TW + 1] once S is dead
 #ifndef CUSIM
     if (G.use_tma) {                                                         // the window is on its way while the tap tables are set up
@@ -1074,13 +1076,14 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     if (tid < V3_TW) {
         const int ox = ox0 + tid;
         const bool ok = ox < P.ow;
-        s_hfirst[tid] = P.h_first[min(ox, P.ow - 1)] - ix0;       // columns past the image edge repeat the last one (zero weights): the walk stays monotone
+        s_hlast[tid] = P.h_first[min(ox, P.ow - 1)] - ix0 + HC - 1;   // columns past the image edge repeat the last one (zero weights): the walk stays monotone
+        if (tid == 0) { s_hlast[V3_TW] = -1; s_vlast[V3_TH] = -1; }
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_hc[tid * 8 + i] = (ok && i < P.h_widest) ? P.h_coeff[(long long)ox * P.h_widest + i] : 0.0f;
     } else if (tid < V3_TW + V3_TH) {
         const int t = tid - V3_TW, oy = oy0 + t;
         const bool ok = oy < P.oh;
-        s_vfirst[t] = P.v_first[min(oy, P.oh - 1)] - iy0;
+        s_vlast[t] = P.v_first[min(oy, P.oh - 1)] - iy0 + VC - 1;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_vc[t * 8 + i] = (ok && i < P.v_widest) ? P.v_coeff[(long long)oy * P.v_widest + i] : 0.0f;
     }
@@ -1133,7 +1136,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     uint32_t amask = 0xffffffffu;                                            // AND of every pixel this thread reads
     {
         const int j0 = (wid >> 1) * 8, j1 = j0 + 8;
-        const int f0 = s_vfirst[j0], rend = s_vfirst[j1 - 1] + VC;            // input rows [f0, rend) of the window
+        const int f0 = s_vlast[j0] - (VC - 1), rend = s_vlast[j1 - 1] + 1;    // input rows [f0, rend) of the window
         for (int cp = (wid & 1) * 32 + lane; cp < ncp; cp += 64) {
             F2 w0[VC], w1[VC], wb[VC];
             int j = j0, ej = f0 + VC - 1;                                      // next output row and its last input row
@@ -1149,7 +1152,10 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                         w0[sl] = byte_pair<EXACT>(pp.x, sel_r, pp.x, sel_g);
                         w1[sl] = byte_pair<EXACT>(pp.y, sel_r, pp.y, sel_g);
                         wb[sl] = byte_pair<EXACT>(pp.x, sel_b, pp.y, sel_b);
-                        while (j < j1 && ej == r) {                           // uniform: every thread walks the same rows
+                        // uniform: every thread walks the same rows.  No j < j1 test: a row of the NEXT group completing at this
+                        // very input row (only when enlarging) has exactly this window as its taps -- the duplicate write
+                        // stores the same values the owner stores; the sentinel ends the walk at the tile's last row.
+                        while (ej == r) {
                             const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + j * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + j * 8 + 4);
                             const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                             F2 a0 = f2_mul<EXACT>(w0[(sl + 1) % VC], vc[0]), a1 = f2_mul<EXACT>(w1[(sl + 1) % VC], vc[0]);
@@ -1165,7 +1171,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                             float *tb = TB + j * tp + 2 * cp;
                             tb[0] = ab.x; tb[1] = ab.y;
                             ++j;
-                            ej = j < j1 ? s_vfirst[j] + VC - 1 : -1;
+                            ej = s_vlast[j];
                         }
                     }
                 }
@@ -1194,7 +1200,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
     }
     {
         const int tx0 = wid * 8, tx1 = tx0 + 8;
-        const int f0 = s_hfirst[tx0], cend = s_hfirst[tx1 - 1] + HC;
+        const int f0 = s_hlast[tx0] - (HC - 1), cend = s_hlast[tx1 - 1] + 1;
         const float2 *trow = TRG + lane * tp;
         const float *brow = TB + lane * tp;
         F2 wrg[HC]; float wbb[HC];
@@ -1207,7 +1213,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                 if (c < cend) {
                     const float2 q = trow[c];
                     wrg[sl] = F2{q.x, q.y}; wbb[sl] = brow[c];
-                    while (tx < tx1 && etx == c) {
+                    while (etx == c) {                                         // same argument as in the vertical walk
                         const float4 h0 = *reinterpret_cast<const float4 *>(s_hc + tx * 8), h1 = *reinterpret_cast<const float4 *>(s_hc + tx * 8 + 4);
                         const float hc[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                         F2 c2; float cb, al = 1.0f;
@@ -1246,7 +1252,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                         }
                         O[lane * (V3_TW + 1) + tx] = px;
                         ++tx;
-                        etx = tx < tx1 ? s_hfirst[tx] + HC - 1 : -1;
+                        etx = s_hlast[tx];
                     }
                 }
             }
@@ -1429,7 +1435,7 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
             const int ntx3 = (int)tix3.size();
             const int sp3 = (nix3 + 3) & ~3, tp3 = sp3 | 1;
             const size_t v3smem = sizeof(uint32_t) * (size_t)niy * sp3 + (sizeof(float2) + sizeof(float)) * (size_t)V3_TH * tp3 + 16 +
-                                  sizeof(float) * ((size_t)V3_TW * 8 + V3_TH * 8) + sizeof(int) * (V3_TW + V3_TH);
+                                  sizeof(float) * ((size_t)V3_TW * 8 + V3_TH * 8) + sizeof(int) * (V3_TW + V3_TH + 2);
             // v3 pays off in the FAST arithmetic (5.4 vs 7.9 ms per 148 C2 frames); in EXACT arithmetic its streaming passes are
             // slower than the planar kernel (9.3 vs 7.9 ms), so bit-exact scaling stays on the planar kernel unless asked
             const bool v3_ok = planar_ok && !getenv("B200TIMG_NO_V3") && (fast || getenv("B200TIMG_V3_EXACT")) && v3smem <= 100 * 1024 &&
