@@ -710,6 +710,152 @@ sixel_emit_kernel(EmitGeom G, SixelWork W) {
     });
 }
 
+// ---- emit v1b: one walk instead of two -------------------------------------------------------------------------------
+// profiles/r2_lines_sixel_emit_v1.txt: v1 spends ~21 % of its instructions in the sizes walk and ~31 % in the byte-wise,
+// heavily divergent formatting of the write walk (every lane of a warp sits in another branch of put_rle / put_num4 and
+// stores single bytes to global memory).  v1b walks the sorted entries ONCE: every run head builds its <= 3 pieces
+// (colour introducer, gap, run) as 64-bit values with branch-light arithmetic and appends them to a thread-private slot
+// in shared memory (word-interleaved over the threads, so the stores are conflict-free; the <= 3 words a piece touches
+// are all stored, no branches); the slot's fill IS the thread's size, and after the block scan the slot is copied out with
+// aligned 4-byte stores.  The slots take over the sort's count/mask tables.  A thread whose bytes do not fit its slot
+// (noise frames) falls back to v1's write walk for its own range.
+constexpr int SLOT_WORDS = 22;                   // words of a slot
+constexpr uint32_t SLOT_MAX = 4 * (SLOT_WORDS - 3);   // an append may START at byte <= SLOT_MAX (it touches <= 3 words)
+static_assert(SLOT_WORDS * ET >= 2 * EW * 256, "the slots alias the sort's tables");
+
+__device__ __forceinline__ uint32_t dec4(uint32_t v, uint32_t nd) {      // digits of v < 10000, most significant first, nd bytes
+    const uint32_t q1 = v / 10u, q2 = q1 / 10u, q3 = q2 / 10u;
+    const uint32_t full = 0x30303030u + (q3 | ((q2 - q3 * 10u) << 8) | ((q1 - q2 * 10u) << 16) | ((v - q1 * 10u) << 24));
+    return full >> (8u * (4u - nd));
+}
+__device__ __forceinline__ unsigned long long rle_piece4(uint32_t n, uint32_t ch, uint32_t &len) {   // tosixel.c sixel_put_flash
+    if (n > 3u) {
+        const uint32_t nd = ndig4(n);
+        len = 2u + nd;
+        return 0x21ull | ((unsigned long long)dec4(n, nd) << 8) | ((unsigned long long)ch << (8u * (1u + nd)));
+    }
+    len = n;
+    return (unsigned long long)((ch * 0x010101u) & ((1u << (8u * n)) - 1u));
+}
+// append the first len (<= 7) bytes of v (zero above them) at byte `pos` of the slot; `cur` = the partial word at pos
+__device__ __forceinline__ void slot_append(uint32_t *slot, uint32_t &pos, uint32_t &cur, unsigned long long v, uint32_t len) {
+    const uint32_t sh = 8u * (pos & 3u);
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const uint32_t w0 = cur | (lo << sh);
+    const uint32_t w1 = __funnelshift_l(lo, hi, sh);
+    const uint32_t w2 = sh ? (hi >> (32u - sh)) : 0u;
+    uint32_t *p = slot + min(pos >> 2, (uint32_t)(SLOT_WORDS - 3)) * ET;   // clamped: an overflowing thread only needs its byte count
+    p[0] = w0; p[ET] = w1; p[2 * ET] = w2;
+    const uint32_t np = pos + len, adv = (np >> 2) - (pos >> 2);
+    const uint32_t part = adv == 0u ? w0 : (adv == 1u ? w1 : w2);
+    cur = part & ((1u << (8u * (np & 3u))) - 1u);
+    pos = np;
+}
+
+__global__ void __launch_bounds__(ET, 2)
+sixel_emit1b_kernel(EmitGeom G, SixelWork W) {
+    extern __shared__ uint32_t s_sorted[];                   // [6*w]
+    __shared__ uint32_t s_tab[SLOT_WORDS * ET];              // sort: cnt[EW][256] | mask[EW][256]; afterwards: slots
+    __shared__ uint32_t s_w[ET / 32];
+    const int band = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int w = G.w;
+    const uint8_t *idx = W.index + ((long long)f * G.h + (long long)band * 6) * w;
+
+    for (int i = tid; i < 2 * EW * 256; i += ET) s_tab[i] = 0;
+    __syncthreads();
+    // (1) the sort: as in v1
+    const int x_lo = wid * G.cols_per_warp, x_hi = min(w, x_lo + G.cols_per_warp);
+    uint32_t *cnt = s_tab + wid * 256, *M = s_tab + EW * 256 + wid * 256;
+    for (int x = x_lo + lane; x < x_hi; x += 32) {
+        uint32_t col[6], bits[6];
+        const uint32_t valid = column_entries(idx, w, x, col, bits);
+#pragma unroll
+        for (int s = 0; s < 6; ++s) if (valid & (1u << s)) atomicAdd(&cnt[col[s]], 1u);
+    }
+    __syncthreads();
+    uint32_t tot_c = 0;
+    if (tid < 256) for (int k = 0; k < EW; ++k) tot_c += s_tab[k * 256 + tid];
+    uint32_t n_ent; const uint32_t cb = block_excl_scan<ET>(tid < 256 ? tot_c : 0, s_w, n_ent);
+    if (tid < 256) {
+        uint32_t run = cb;
+        for (int k = 0; k < EW; ++k) { const uint32_t v = s_tab[k * 256 + tid]; s_tab[k * 256 + tid] = run; run += v; }
+    }
+    __syncthreads();
+    const uint32_t lt = (1u << lane) - 1;
+    for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
+        const int x = x0 + lane;
+        uint32_t col[6], bits[6];
+        const uint32_t valid = x < x_hi ? column_entries(idx, w, x, col, bits) : 0u;
+#pragma unroll
+        for (int s = 0; s < 6; ++s) if (valid & (1u << s)) atomicOr(&M[col[s]], 1u << lane);
+        __syncwarp();
+        uint32_t mk[6];
+#pragma unroll
+        for (int s = 0; s < 6; ++s)
+            if (valid & (1u << s)) {
+                mk[s] = M[col[s]];
+                s_sorted[cnt[col[s]] + __popc(mk[s] & lt)] = ent_pack(col[s], (uint32_t)x, bits[s]);
+            }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 6; ++s)
+            if ((valid & (1u << s)) && (mk[s] & lt) == 0) { cnt[col[s]] += (uint32_t)__popc(mk[s]); M[col[s]] = 0; }
+        __syncwarp();
+    }
+    __syncthreads();                                         // the tables are dead: s_tab is the slot array from here on
+    // (2) one walk: bytes into the slot, size = the slot's fill
+    const int n = (int)n_ent;
+    const uint32_t minc = s_sorted[0] >> 18;
+    const int per = (n + ET - 1) / ET, lo = min(n, tid * per), hi = min(n, lo + per);
+    uint32_t *slot = s_tab + tid;
+    uint32_t pos = 0, cur = 0;
+    bool ovf = false;
+    walk_runs(s_sorted, lo, hi, n, [&](uint32_t c, uint32_t bits, uint32_t gap, uint32_t len, bool first) {
+        uint32_t pl;
+        if (first) {
+            const uint32_t nd = ndig4(c);
+            unsigned long long v = 0x23ull | ((unsigned long long)dec4(c, nd) << 8);
+            pl = 1u + nd;
+            if (c != minc) { v = 0x24ull | (v << 8); ++pl; }
+            ovf |= pos > SLOT_MAX;
+            slot_append(slot, pos, cur, v, pl);
+        }
+        unsigned long long v = rle_piece4(gap, 0x3fu, pl);
+        ovf |= pos > SLOT_MAX;
+        slot_append(slot, pos, cur, v, pl);
+        v = rle_piece4(len, 0x3fu + bits, pl);
+        ovf |= pos > SLOT_MAX;
+        slot_append(slot, pos, cur, v, pl);
+    });
+    const uint32_t local = pos;
+    uint32_t band_total; const uint32_t at = block_excl_scan<ET>(local, s_w, band_total);
+    if (tid == 0) W.band_bytes[(long long)f * W.nbands + band] = band_total;
+    // (3) the slot's bytes into this band's scratch place (16-byte aligned base): head bytes up to a word boundary, whole
+    // words realigned with a funnel shift, tail bytes
+    char *o = W.scratch + ((size_t)f * W.nbands + band) * W.band_cap + at;
+    if (!ovf) {
+        const uint32_t head = min(local, (4u - (at & 3u)) & 3u);
+        const uint32_t w0 = slot[0];
+        for (uint32_t k = 0; k < head; ++k) o[k] = (char)(w0 >> (8u * k));
+        const uint32_t nw = (local - head) >> 2;
+        uint32_t *dw = reinterpret_cast<uint32_t *>(o + head);
+        uint32_t a = w0;
+        for (uint32_t j = 0; j < nw; ++j) {
+            const uint32_t b = slot[(j + 1) * ET];
+            dw[j] = __funnelshift_r(a, b, 8u * head);
+            a = b;
+        }
+        const uint32_t done = head + 4u * nw;                // a = the slot word holding byte `done - head`... see below
+        for (uint32_t k = done; k < local; ++k) o[k] = (char)(slot[(k >> 2) * ET] >> (8u * (k & 3u)));
+    } else {                                                 // v1's write walk for this thread's range
+        walk_runs(s_sorted, lo, hi, n, [&](uint32_t c, uint32_t bits, uint32_t gap, uint32_t len, bool first) {
+            if (first) { if (c != minc) *o++ = '$'; *o++ = '#'; o = put_num4(o, c); }
+            o = put_rle(o, gap, '?');
+            o = put_rle(o, len, (char)('?' + bits));
+        });
+    }
+}
+
 // per frame: header length, band offsets (exclusive, in place), frame size
 __global__ void __launch_bounds__(256)
 sixel_layout_kernel(int w, int h, SixelWork W) {
@@ -861,12 +1007,13 @@ static int sixel_plan(b200timg_ctx *ctx, int w, int h, int n_frames, bool reserv
     // look-back against v1's 5.2 + 0.36 ms per 148 C2 frames; kept for A/B runs only).
     {
         const bool v1_fits = w <= 4095 && sizeof(uint32_t) * (size_t)6 * w <= (size_t)(227 - 36) * 1024;
-        int mode = v1_fits ? 1 : 2;
+        const bool v1b_fits = w <= 4095 && sizeof(uint32_t) * (size_t)6 * w <= (size_t)(227 - 47) * 1024;
+        int mode = v1b_fits ? 4 : v1_fits ? 1 : 2;           // 4 = v1b: v1 with the single formatting walk
         if (getenv("B200TIMG_EMIT_V2")) mode = 2;
         if (const char *e = getenv("B200TIMG_EMIT")) mode = atoi(e);
-        if (mode < 1 || mode > 3 || (mode == 1 && !v1_fits)) mode = 2;
+        if (mode < 1 || mode > 4 || (mode == 1 && !v1_fits) || (mode == 4 && !v1b_fits)) mode = 2;
         S->emit_mode = mode;
-        S->emit_v1 = mode == 1;
+        S->emit_v1 = mode == 1 || mode == 4;
     }
     if (S->emit_v1) off += W.band_cap * W.nbands * n_frames;
     S->dither_v1 = getenv("B200TIMG_DITHER_V1") != nullptr;      // round-1 ditherer, kept for A/B runs
@@ -893,6 +1040,7 @@ static int sixel_plan(b200timg_ctx *ctx, int w, int h, int n_frames, bool reserv
     if (!ctx->sixel_attrs_set) {                         // function attributes are per device, i.e. per context
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+        B2_CUDA(ctx, cudaFuncSetAttribute(sixel_emit1b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (227 - 47) * 1024));
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_dither_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + DW_MAX * DWARP_SMEM));
         // unconditionally: which variant a frame takes depends on ITS size, not on the first frame this context saw
         B2_CUDA(ctx, cudaFuncSetAttribute(sixel_palette_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -945,7 +1093,8 @@ int launch_sixel_front(b200timg_ctx *ctx, const uint8_t *d_fb, int w, int h, int
     }
     if (S.emit_v1) {
         B2_KERNEL(ctx, "sixel_emit_kernel");
-        sixel_emit_kernel<<<dim3(W.nbands, n), ET, S.emit_smem, ctx->stream>>>(S.G, W);
+        if (S.emit_mode == 4) sixel_emit1b_kernel<<<dim3(W.nbands, n), ET, S.emit_smem, ctx->stream>>>(S.G, W);
+        else sixel_emit_kernel<<<dim3(W.nbands, n), ET, S.emit_smem, ctx->stream>>>(S.G, W);
         B2_LAUNCH_CHECK(ctx);
     }
     return B200TIMG_OK;
