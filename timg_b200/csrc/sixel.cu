@@ -723,21 +723,35 @@ constexpr int SLOT_WORDS = 22;                   // words of a slot
 constexpr uint32_t SLOT_MAX = 4 * (SLOT_WORDS - 3);   // an append may START at byte <= SLOT_MAX (it touches <= 3 words)
 static_assert(SLOT_WORDS * ET >= 2 * EW * 256, "the slots alias the sort's tables");
 
-__device__ __forceinline__ uint32_t dec4(uint32_t v, uint32_t nd) {      // digits of v < 10000, most significant first, nd bytes
-    const uint32_t q1 = v / 10u, q2 = q1 / 10u, q3 = q2 / 10u;
-    const uint32_t full = 0x30303030u + (q3 | ((q2 - q3 * 10u) << 8) | ((q1 - q2 * 10u) << 16) | ((v - q1 * 10u) << 24));
-    return full >> (8u * (4u - nd));
+// decimal strings of 0..4095 (run lengths, gaps and colour numbers of a <= 4095 px wide band): the digits, most significant
+// first, as a little-endian byte string, zero above them.  Built at compile time, read through the L1.
+struct DecTable { uint32_t v[4096]; };
+constexpr DecTable make_dec_table() {
+    DecTable t{};
+    for (uint32_t n = 0; n < 4096; ++n) {
+        uint32_t s = 0, m = n, nd = 0;
+        do { s = (s << 8) | (0x30u + m % 10u); m /= 10u; ++nd; } while (m);          // last digit ends up in the top byte of the nd used
+        t.v[n] = s;
+    }
+    return t;
+}
+__device__ const DecTable k_dec = make_dec_table();
+__device__ __forceinline__ uint32_t dec4(uint32_t v, uint32_t &nd) {     // v < 4096
+    const uint32_t s = __ldg(&k_dec.v[v]);
+    nd = 4u - ((uint32_t)__clz((int)s) >> 3);
+    return s;
 }
 __device__ __forceinline__ unsigned long long rle_piece4(uint32_t n, uint32_t ch, uint32_t &len) {   // tosixel.c sixel_put_flash
     if (n > 3u) {
-        const uint32_t nd = ndig4(n);
+        uint32_t nd;
+        const uint32_t d = dec4(n, nd);
         len = 2u + nd;
-        return 0x21ull | ((unsigned long long)dec4(n, nd) << 8) | ((unsigned long long)ch << (8u * (1u + nd)));
+        return 0x21ull | ((unsigned long long)d << 8) | ((unsigned long long)ch << (8u * (1u + nd)));
     }
     len = n;
     return (unsigned long long)((ch * 0x010101u) & ((1u << (8u * n)) - 1u));
 }
-// append the first len (<= 7) bytes of v (zero above them) at byte `pos` of the slot; `cur` = the partial word at pos
+// append the first len (<= 8) bytes of v (zero above them) at byte `pos` of the slot; `cur` = the partial word at pos
 __device__ __forceinline__ void slot_append(uint32_t *slot, uint32_t &pos, uint32_t &cur, unsigned long long v, uint32_t len) {
     const uint32_t sh = 8u * (pos & 3u);
     const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
@@ -747,8 +761,7 @@ __device__ __forceinline__ void slot_append(uint32_t *slot, uint32_t &pos, uint3
     uint32_t *p = slot + min(pos >> 2, (uint32_t)(SLOT_WORDS - 3)) * ET;   // clamped: an overflowing thread only needs its byte count
     p[0] = w0; p[ET] = w1; p[2 * ET] = w2;
     const uint32_t np = pos + len, adv = (np >> 2) - (pos >> 2);
-    const uint32_t part = adv == 0u ? w0 : (adv == 1u ? w1 : w2);
-    cur = part & ((1u << (8u * (np & 3u))) - 1u);
+    cur = adv == 0u ? w0 : (adv == 1u ? w1 : w2);            // v is zero above len: the word at np holds nothing beyond np
     pos = np;
 }
 
@@ -813,19 +826,23 @@ sixel_emit1b_kernel(EmitGeom G, SixelWork W) {
     walk_runs(s_sorted, lo, hi, n, [&](uint32_t c, uint32_t bits, uint32_t gap, uint32_t len, bool first) {
         uint32_t pl;
         if (first) {
-            const uint32_t nd = ndig4(c);
+            uint32_t nd;
             unsigned long long v = 0x23ull | ((unsigned long long)dec4(c, nd) << 8);
             pl = 1u + nd;
             if (c != minc) { v = 0x24ull | (v << 8); ++pl; }
             ovf |= pos > SLOT_MAX;
             slot_append(slot, pos, cur, v, pl);
         }
-        unsigned long long v = rle_piece4(gap, 0x3fu, pl);
+        uint32_t rl;
+        const unsigned long long gv = rle_piece4(gap, 0x3fu, pl), rv = rle_piece4(len, 0x3fu + bits, rl);
         ovf |= pos > SLOT_MAX;
-        slot_append(slot, pos, cur, v, pl);
-        v = rle_piece4(len, 0x3fu + bits, pl);
-        ovf |= pos > SLOT_MAX;
-        slot_append(slot, pos, cur, v, pl);
+        if (pl + rl <= 8u) {                                 // nearly always: blank columns + run in one append
+            slot_append(slot, pos, cur, gv | (rv << (8u * pl)), pl + rl);
+        } else {
+            slot_append(slot, pos, cur, gv, pl);
+            ovf |= pos > SLOT_MAX;
+            slot_append(slot, pos, cur, rv, rl);
+        }
     });
     const uint32_t local = pos;
     uint32_t band_total; const uint32_t at = block_excl_scan<ET>(local, s_w, band_total);
