@@ -890,6 +890,48 @@ twopass_h1_kernel(const uint32_t *__restrict__ in, TwoPassParams T) {
     }
     T.tmp[((long long)f * P.ih + y) * P.ow + ox] = r;
 }
+// pass 1, horizontal first, STAGED: the same sums as twopass_h1_kernel, but a warp decodes the stretch of its source row
+// that the CTA's 32 output columns need ONCE into shared memory (coalesced 128-byte loads) and the taps then read
+// float4s from there -- the plain kernel decodes every source pixel once per output that uses it (~4x for the long
+// filters this path serves) through uncoalesced 4-byte loads.  warp = source row, lane = output column.
+struct H1sGeom { int nwin, cpitch; };            // window columns per tile (max over tiles), coefficient pitch (odd)
+template <bool PLAIN>
+__global__ void __launch_bounds__(256)
+twopass_h1s_kernel(const uint32_t *__restrict__ in, TwoPassParams T, H1sGeom G) {
+    extern __shared__ float4 s_h1[];                                     // [8][nwin] decoded pixels | [32][cpitch] coefficients
+    const ResampleParams &P = T.P;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, f = blockIdx.z;
+    if (PLAIN && !T.need_plain[f]) return;
+    const int ox0 = blockIdx.x * 32, ox = ox0 + lane, y = blockIdx.y * 8 + wid;
+    float *s_c = reinterpret_cast<float *>(s_h1 + 8 * G.nwin);
+    for (int i = threadIdx.x; i < 32 * P.h_widest; i += 256) {
+        const int o = i / P.h_widest, k = i - o * P.h_widest;
+        s_c[o * G.cpitch + k] = ox0 + o < P.ow ? P.h_coeff[(long long)(ox0 + o) * P.h_widest + k] : 0.0f;
+    }
+    const int c0 = P.h_first[ox0];
+    if (y < P.ih) {
+        const uint32_t *row = in + (long long)f * P.iw * P.ih + (long long)y * P.iw;
+        float4 *srow = s_h1 + wid * G.nwin;
+        const int c1 = min(P.iw, c0 + G.nwin);
+        for (int c = c0 + lane; c < c1; c += 32) srow[c - c0] = decode_tp<PLAIN>(row[c], P.bgra);
+    }
+    __syncthreads();
+    if (ox >= P.ow || y >= P.ih) return;
+    const float4 *v = s_h1 + wid * G.nwin + (P.h_first[ox] - c0);
+    const float *hc = s_c + lane * G.cpitch;
+    const int cnt = P.h_count[ox];
+    float4 r;
+    if (P.h_sequential) {
+        r = mul4(v[0], hc[0]);
+        for (int i = 1; i < cnt; ++i) r = add4(r, mul4(v[i], hc[i]));
+    } else {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a0 = z, a1 = z;
+        for (int i = 0; i < cnt; ++i) { const float4 t = mul4(v[i], hc[i]); if (i & 1) a1 = add4(a1, t); else a0 = add4(a0, t); }
+        r = add4(a0, a1);
+    }
+    T.tmp[((long long)f * P.ih + y) * P.ow + ox] = r;
+}
 // pass 2: filter the intermediate along the other axis, then un-weight / encode / compose (weighted pass) or
 // fill in the pixels whose alpha came out as zero (plain pass)
 template <bool VFIRST, bool PLAIN>
@@ -1535,8 +1577,24 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
                     B2_LAUNCH_CHECK(ctx);
                 } else {
                     const dim3 g1((ow + 31) / 32, (ih + 7) / 8, n_frames);
+                    // staged variant: window of a 32-column tile = first[tile start] .. max(first + count) over the tile
+                    H1sGeom HG{1, pl->h.widest | 1};
+                    for (int x0 = 0; x0 < ow; x0 += 32) {
+                        int hi = 0;
+                        for (int x = x0; x < std::min(ow, x0 + 32); ++x) hi = std::max(hi, pl->h.first[x] + pl->h.count[x]);
+                        HG.nwin = std::max(HG.nwin, hi - pl->h.first[x0]);
+                    }
+                    const size_t h1smem = sizeof(float4) * 8 * (size_t)HG.nwin + sizeof(float) * 32 * (size_t)HG.cpitch;
                     B2_KERNEL(ctx, plain ? "twopass_plain_kernels" : "twopass_h1_kernel");
-                    if (plain) twopass_h1_kernel<true><<<g1, 256, 0, ctx->stream>>>(in, T); else twopass_h1_kernel<false><<<g1, 256, 0, ctx->stream>>>(in, T);
+                    if (h1smem <= 72 * 1024 && !getenv("B200TIMG_NO_H1S")) {
+                        if (plain) {
+                            B2_CUDA(ctx, cudaFuncSetAttribute(twopass_h1s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                            twopass_h1s_kernel<true><<<g1, 256, h1smem, ctx->stream>>>(in, T, HG);
+                        } else {
+                            B2_CUDA(ctx, cudaFuncSetAttribute(twopass_h1s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                            twopass_h1s_kernel<false><<<g1, 256, h1smem, ctx->stream>>>(in, T, HG);
+                        }
+                    } else if (plain) twopass_h1_kernel<true><<<g1, 256, 0, ctx->stream>>>(in, T); else twopass_h1_kernel<false><<<g1, 256, 0, ctx->stream>>>(in, T);
                     B2_LAUNCH_CHECK(ctx);
                     B2_KERNEL(ctx, plain ? "twopass_plain_kernels" : "twopass_2_kernel");
                     if (plain) twopass_2_kernel<false, true><<<g2, 256, 0, ctx->stream>>>(out, T); else twopass_2_kernel<false, false><<<g2, 256, 0, ctx->stream>>>(out, T);
