@@ -1083,7 +1083,18 @@ __device__ __forceinline__ uint32_t sat_u8(float v) {
 }
 
 struct V3Geom { int nix, niy, sp, tp; unsigned grp_magic; const int32_t *tile_ix0, *tile_iy0; uint32_t *fallback; int use_tma; };   // grp_magic: floor(2^32/(sp/4))+1
-constexpr int V3_TW = 64, V3_TH = 32, V3_NT = 256, V3_MINB = 3;   // 3 CTAs/SM: <= 80 registers (84 cost a third of the occupancy: 5.06 -> 6.05 ms)
+// Tuning switches (tools/build_variant.sh builds variant libraries; measured per 148 C2 frames, run r2k):
+//   V3_SENT 0, 2 CTAs/SM asked (78 registers, 3 resident anyway)   4.70 ms   <- default
+//   V3_SENT 1, 3 CTAs/SM forced (72 registers, more instructions)  5.36 ms
+//   V3_SENT 1, 2 CTAs/SM (84 registers: only 2 resident)           6.05 ms
+//   V3_SENT 0, 3 CTAs/SM forced (80 registers, spills)             6.03 ms
+#ifndef V3_SENT
+#define V3_SENT 0            // 1: sentinel-terminated completion walks (no bound test), 0: bounded walks
+#endif
+#ifndef V3_MINB_VALUE
+#define V3_MINB_VALUE 2
+#endif
+constexpr int V3_TW = 64, V3_TH = 32, V3_NT = 256, V3_MINB = V3_MINB_VALUE;   // 3 CTAs/SM: <= 80 registers (84 cost a third of the occupancy: 5.06 -> 6.05 ms)
 
 template <int HC, int VC, bool EXACT>
 __global__ void __launch_bounds__(V3_NT, (VC >= 8 ? 2 : V3_MINB))      // the 8-row register windows do not fit 80 registers
@@ -1197,7 +1208,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                         // uniform: every thread walks the same rows.  No j < j1 test: a row of the NEXT group completing at this
                         // very input row (only when enlarging) has exactly this window as its taps -- the duplicate write
                         // stores the same values the owner stores; the sentinel ends the walk at the tile's last row.
-                        while (ej == r) {
+                        while ((V3_SENT || j < j1) && ej == r) {
                             const float4 v0 = *reinterpret_cast<const float4 *>(s_vc + j * 8), v1 = *reinterpret_cast<const float4 *>(s_vc + j * 8 + 4);
                             const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                             F2 a0 = f2_mul<EXACT>(w0[(sl + 1) % VC], vc[0]), a1 = f2_mul<EXACT>(w1[(sl + 1) % VC], vc[0]);
@@ -1213,7 +1224,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                             float *tb = TB + j * tp + 2 * cp;
                             tb[0] = ab.x; tb[1] = ab.y;
                             ++j;
-                            ej = s_vlast[j];
+                            ej = (V3_SENT || j < j1) ? s_vlast[j] : -1;
                         }
                     }
                 }
@@ -1255,7 +1266,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                 if (c < cend) {
                     const float2 q = trow[c];
                     wrg[sl] = F2{q.x, q.y}; wbb[sl] = brow[c];
-                    while (etx == c) {                                         // same argument as in the vertical walk
+                    while ((V3_SENT || tx < tx1) && etx == c) {                // same argument as in the vertical walk
                         const float4 h0 = *reinterpret_cast<const float4 *>(s_hc + tx * 8), h1 = *reinterpret_cast<const float4 *>(s_hc + tx * 8 + 4);
                         const float hc[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                         F2 c2; float cb, al = 1.0f;
@@ -1294,7 +1305,7 @@ resample_v3_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, 
                         }
                         O[lane * (V3_TW + 1) + tx] = px;
                         ++tx;
-                        etx = s_hlast[tx];
+                        etx = (V3_SENT || tx < tx1) ? s_hlast[tx] : -1;
                     }
                 }
             }
@@ -1586,7 +1597,10 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
                     }
                     const size_t h1smem = sizeof(float4) * 8 * (size_t)HG.nwin + sizeof(float) * 32 * (size_t)HG.cpitch;
                     B2_KERNEL(ctx, plain ? "twopass_plain_kernels" : "twopass_h1_kernel");
-                    if (h1smem <= 72 * 1024 && !getenv("B200TIMG_NO_H1S")) {
+                    // staging pays when the 32-column tiles are mostly full (4K -> 337 columns: 6.53 -> 5.42 ms per 128 frames); with
+                    // 67 columns the third tile stages a whole window for 3 outputs (8.23 -> 8.73 ms per 4096 frames): plain kernel
+                    const bool tiles_full = (long long)((ow + 31) / 32) * 32 * 100 <= (long long)ow * 115;
+                    if (h1smem <= 72 * 1024 && tiles_full && !getenv("B200TIMG_NO_H1S")) {
                         if (plain) {
                             B2_CUDA(ctx, cudaFuncSetAttribute(twopass_h1s_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
                             twopass_h1s_kernel<true><<<g1, 256, h1smem, ctx->stream>>>(in, T, HG);
