@@ -92,7 +92,9 @@ sixel_dither2_kernel(const uint32_t *__restrict__ fb, Dither2Geom G, SixelWork W
     uint8_t *index = W.index + (long long)f * w * h;
     uint4 *bnd = bnd_all + (long long)f * G.nb32 * w;
     volatile int *gprog = gprog_all + (long long)f * G.nb32;
-    const int hrow = lane >> 4, hcol = lane & 15;                // half-warp staging coordinates
+    const int hrow = lane >> 4, hcol = lane & 15;                // half-warp staging coordinates (odd widths)
+    const int qrow = lane >> 3, qcol = lane & 7;                 // quarter-warp staging coordinates (even widths: pixel pairs)
+    const bool even_w = (w & 1) == 0;
     const TapW Z = {0u, 0u, 0u};
 
     for (int band = band_lo + wid; band < band_hi; band += G.nwarps) {
@@ -105,18 +107,38 @@ sixel_dither2_kernel(const uint32_t *__restrict__ fb, Dither2Geom G, SixelWork W
         uint4 *bout = bnd + (long long)band * w;
         TapW own = Z, a0 = Z, a1 = Z, a2 = Z, e_first = Z;
         const int steps = w + 62, nchunks = (steps + D2_CH - 1) / D2_CH;
+        // staging of a chunk (16 skewed columns x 32 rows).  Even widths: 8 lanes per row, a pixel PAIR per lane (8-byte loads,
+        // half the load instructions: the frame loads were 11 % of the kernel's instructions); odd widths: 16 lanes per row.
         uint32_t pre[16];
         auto load_chunk = [&](int c) {
+            if (even_w) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int r = 2 * i + hrow, yy = band * 32 + r, x = c * D2_CH - 2 * r + hcol;
-                pre[i] = (yy < h && x >= 0 && x < w) ? frame[(long long)yy * w + x] : 0u;
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + qrow, yy = band * 32 + r, x = c * D2_CH - 2 * r + 2 * qcol;
+                    uint2 v = make_uint2(0u, 0u);
+                    if (yy < h && x >= 0 && x < w) v = *reinterpret_cast<const uint2 *>(frame + (long long)yy * w + x);
+                    pre[2 * i] = v.x; pre[2 * i + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int r = 2 * i + hrow, yy = band * 32 + r, x = c * D2_CH - 2 * r + hcol;
+                    pre[i] = (yy < h && x >= 0 && x < w) ? frame[(long long)yy * w + x] : 0u;
+                }
             }
         };
         auto store_chunk = [&](int c) {
             uint32_t *t = s_in + (c & 1) * 32 * D2_IN_STRIDE;
+            if (even_w) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) t[(2 * i + hrow) * D2_IN_STRIDE + hcol] = pre[i];
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t *q = t + (4 * i + qrow) * D2_IN_STRIDE + 2 * qcol;
+                    q[0] = pre[2 * i]; q[1] = pre[2 * i + 1];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[(2 * i + hrow) * D2_IN_STRIDE + hcol] = pre[i];
+            }
         };
         load_chunk(0); store_chunk(0);
         __syncwarp();
@@ -193,11 +215,21 @@ sixel_dither2_kernel(const uint32_t *__restrict__ fb, Dither2Geom G, SixelWork W
                 }
             }
             __syncwarp();
-            // write this chunk's indices: half-warp per row, 16 contiguous bytes
+            // write this chunk's indices: 16 contiguous bytes per row -- as 8 two-byte stores (even widths) or 16 single bytes
+            if (even_w) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int r = 2 * i + hrow, yy = band * 32 + r, x = t0 - 2 * r + hcol;
-                if (yy < h && x >= 0 && x < w) index[(long long)yy * w + x] = s_out[r * D2_OUT_STRIDE + hcol];
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + qrow, yy = band * 32 + r, x = t0 - 2 * r + 2 * qcol;
+                    if (yy < h && x >= 0 && x < w)
+                        *reinterpret_cast<unsigned short *>(index + (long long)yy * w + x) =
+                            *reinterpret_cast<const unsigned short *>(s_out + r * D2_OUT_STRIDE + 2 * qcol);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int r = 2 * i + hrow, yy = band * 32 + r, x = t0 - 2 * r + hcol;
+                    if (yy < h && x >= 0 && x < w) index[(long long)yy * w + x] = s_out[r * D2_OUT_STRIDE + hcol];
+                }
             }
             {   // publish progress: lane 31's boundary stores of this chunk are ordered before the flag
                 const int done = min(w, t0 + D2_CH - 62);
