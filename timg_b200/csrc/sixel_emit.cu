@@ -333,12 +333,7 @@ constexpr uint32_t E3_WIN = E3_TAB_WORDS * 4 - 640;             // chunks STARTI
 static_assert(E3_WIN + E3_CHUNK_MAX <= E3_TAB_WORDS * 4, "a window must hold its last chunk");
 
 struct Emit3Geom { int w, h, nbands, ntiles, tw, cpw, ent_cap; unsigned n_cta; int dbg; };   // dbg: timing experiments (B200TIMG_E3DBG), output invalid when set
-#ifdef CUSIM
-unsigned long long g_dbg[8];
-#define DBG(i) do { if (lane == 0) ++g_dbg[i]; } while (0)
-#else
-#define DBG(i)
-#endif
+
 
 // decimal digits of v (< 100000), most significant first, as a little-endian byte string of nd bytes
 __device__ __forceinline__ unsigned long long dec5(uint32_t v, uint32_t nd) {
@@ -479,7 +474,6 @@ sixel_emit3_kernel(Emit3Geom G, SixelWork W, uint64_t *__restrict__ offsets, cha
     const bool lead_dollar = tile > 0;
     {
         uint32_t local = 0;
-        for (int ck = c_lo; ck < c_hi; ++ck) DBG(2);
         for (int ck = c_lo; ck < c_hi; ++ck) local += run_step(s_sorted, ck * 32, lane, n, (uint32_t)x0, lead_dollar).size;
         local = __reduce_add_sync(0xffffffffu, local);
         if (lane == 0) s_wtot[wid] = local;
@@ -521,9 +515,7 @@ sixel_emit3_kernel(Emit3Geom G, SixelWork W, uint64_t *__restrict__ offsets, cha
     bool ovf = false;
     int ck = c_lo;
     for (uint32_t win0 = 0;;) {
-        DBG(0);
         while (ck < c_hi && run_off < win0 + E3_WIN) {
-            DBG(1);
             const RunStep r = run_step(s_sorted, ck * 32, lane, n, (uint32_t)x0, lead_dollar);
             const uint32_t incl = warp_incl_scan(r.size, lane);
             uint8_t *p = wbuf + (run_off - win0) + (incl - r.size);
@@ -627,9 +619,6 @@ int launch_sixel_emit3(b200timg_ctx *ctx, int w, int h, int n_frames, const Sixe
     B2_KERNEL(ctx, "sixel_emit3_kernel");
     sixel_emit3_kernel<<<G.n_cta, E3T, smem, ctx->stream>>>(G, W, d_offsets, d_out, (unsigned long long)out_cap);
     B2_LAUNCH_CHECK(ctx);
-#ifdef CUSIM
-    if (getenv("B200TIMG_DBG")) fprintf(stderr, "emit3 dbg: ctas %u window-iterations(warps) %llu chunksB %llu chunksA %llu\n", G.n_cta, g_dbg[0], g_dbg[1], g_dbg[2]);
-#endif
     return B200TIMG_OK;
 }
 
