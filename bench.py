@@ -251,8 +251,8 @@ def main():
         return
 
     numa = pin_to_gpu_numa(local_rank)
-    if world > 1:      # intra-node point-to-point through the copy engines: the gather then takes no SMs from rank 0's kernels
-        os.environ.setdefault("NCCL_P2P_USE_CUDA_MEMCPY", "1")
+    # (NCCL's defaults are left alone: routing the point-to-point gather through the copy engines with
+    # NCCL_P2P_USE_CUDA_MEMCPY=1 measured 18.1 ms per step on 2 GPUs against 14.25 ms with NCCL's own NVLink kernels, run r2n3)
     import torch
     import torch.distributed as dist
     import timg_b200
