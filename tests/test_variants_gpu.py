@@ -38,7 +38,8 @@ def test_tma_staged_window_equals_ldg_staged(ctx, monkeypatch, kind, iw, ih, ow,
     assert d.max() <= 1                                        # the FAST mode's stated tolerance
 
 
-@pytest.mark.parametrize("kind,w,h", [("photo", 675, 384), ("noise", 337, 192), ("photo", 2700, 36), ("alpha", 160, 120)])
+@pytest.mark.parametrize("kind,w,h", [("photo", 675, 384), ("noise", 337, 192), ("photo", 2700, 36), ("alpha", 160, 120),
+                                      ("photo", 3500, 12)])      # > 3072 px: column entries are recomputed, not stashed
 def test_sixel_emitters_agree(ctx, monkeypatch, kind, w, h):
     """v1 and v1b write the same bytes; the single-pass emitters (emit2: other '$' placement, emit3) the same picture."""
     fb = synth.frame_np(900 + w, w, h, kind)

@@ -720,6 +720,7 @@ sixel_emit_kernel(EmitGeom G, SixelWork W) {
 // aligned 4-byte stores.  The slots take over the sort's count/mask tables.  A thread whose bytes do not fit its slot
 // (noise frames) falls back to v1's write walk for its own range.
 constexpr int SLOT_WORDS = 22;                   // words of a slot
+constexpr int STASH_STEPS = 6;                   // 32-column steps of a warp whose column entries stay in registers (w <= 3072)
 constexpr uint32_t SLOT_MAX = 4 * (SLOT_WORDS - 3);   // an append may START at byte <= SLOT_MAX (it touches <= 3 words)
 static_assert(SLOT_WORDS * ET >= 2 * EW * 256, "the slots alias the sort's tables");
 
@@ -776,14 +777,34 @@ sixel_emit1b_kernel(EmitGeom G, SixelWork W) {
 
     for (int i = tid; i < 2 * EW * 256; i += ET) s_tab[i] = 0;
     __syncthreads();
-    // (1) the sort: as in v1
+    // (1) the sort: as in v1, but the column entries (<= 6 distinct colours of a column with their row bits) are computed
+    // once: the count pass parks them in registers (3 words per 32-column step, steps unrolled) for the scatter pass
     const int x_lo = wid * G.cols_per_warp, x_hi = min(w, x_lo + G.cols_per_warp);
     uint32_t *cnt = s_tab + wid * 256, *M = s_tab + EW * 256 + wid * 256;
-    for (int x = x_lo + lane; x < x_hi; x += 32) {
-        uint32_t col[6], bits[6];
-        const uint32_t valid = column_entries(idx, w, x, col, bits);
+    const bool stash = G.cols_per_warp <= 32 * STASH_STEPS;
+    uint32_t k0[STASH_STEPS], k1[STASH_STEPS], k2[STASH_STEPS];     // colours 0-3 | colours 4-5, valid, bits 5 | bits 0-4
+    if (stash) {
 #pragma unroll
-        for (int s = 0; s < 6; ++s) if (valid & (1u << s)) atomicAdd(&cnt[col[s]], 1u);
+        for (int t = 0; t < STASH_STEPS; ++t) {
+            const int x = x_lo + 32 * t + lane;
+            k0[t] = k1[t] = k2[t] = 0;
+            if (x < x_hi) {
+                uint32_t col[6], bits[6];
+                const uint32_t valid = column_entries(idx, w, x, col, bits);
+#pragma unroll
+                for (int s = 0; s < 6; ++s) if (valid & (1u << s)) atomicAdd(&cnt[col[s]], 1u);
+                k0[t] = col[0] | (col[1] << 8) | (col[2] << 16) | (col[3] << 24);
+                k1[t] = col[4] | (col[5] << 8) | (valid << 16) | (bits[5] << 22);
+                k2[t] = bits[0] | (bits[1] << 6) | (bits[2] << 12) | (bits[3] << 18) | (bits[4] << 24);
+            }
+        }
+    } else {
+        for (int x = x_lo + lane; x < x_hi; x += 32) {
+            uint32_t col[6], bits[6];
+            const uint32_t valid = column_entries(idx, w, x, col, bits);
+#pragma unroll
+            for (int s = 0; s < 6; ++s) if (valid & (1u << s)) atomicAdd(&cnt[col[s]], 1u);
+        }
     }
     __syncthreads();
     uint32_t tot_c = 0;
@@ -795,10 +816,7 @@ sixel_emit1b_kernel(EmitGeom G, SixelWork W) {
     }
     __syncthreads();
     const uint32_t lt = (1u << lane) - 1;
-    for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
-        const int x = x0 + lane;
-        uint32_t col[6], bits[6];
-        const uint32_t valid = x < x_hi ? column_entries(idx, w, x, col, bits) : 0u;
+    auto scatter_step = [&](int x, uint32_t valid, const uint32_t *col, const uint32_t *bits) {
 #pragma unroll
         for (int s = 0; s < 6; ++s) if (valid & (1u << s)) atomicOr(&M[col[s]], 1u << lane);
         __syncwarp();
@@ -814,6 +832,23 @@ sixel_emit1b_kernel(EmitGeom G, SixelWork W) {
         for (int s = 0; s < 6; ++s)
             if ((valid & (1u << s)) && (mk[s] & lt) == 0) { cnt[col[s]] += (uint32_t)__popc(mk[s]); M[col[s]] = 0; }
         __syncwarp();
+    };
+    if (stash) {
+#pragma unroll
+        for (int t = 0; t < STASH_STEPS; ++t) {
+            if (x_lo + 32 * t < x_hi) {                      // warp-uniform
+                const uint32_t col[6] = {k0[t] & 255u, (k0[t] >> 8) & 255u, (k0[t] >> 16) & 255u, k0[t] >> 24, k1[t] & 255u, (k1[t] >> 8) & 255u};
+                const uint32_t bits[6] = {k2[t] & 63u, (k2[t] >> 6) & 63u, (k2[t] >> 12) & 63u, (k2[t] >> 18) & 63u, (k2[t] >> 24) & 63u, (k1[t] >> 22) & 63u};
+                scatter_step(x_lo + 32 * t + lane, (k1[t] >> 16) & 63u, col, bits);
+            }
+        }
+    } else {
+        for (int x0 = x_lo; x0 < x_hi; x0 += 32) {
+            const int x = x0 + lane;
+            uint32_t col[6], bits[6];
+            const uint32_t valid = x < x_hi ? column_entries(idx, w, x, col, bits) : 0u;
+            scatter_step(x, valid, col, bits);
+        }
     }
     __syncthreads();                                         // the tables are dead: s_tab is the slot array from here on
     // (2) one walk: bytes into the slot, size = the slot's fill
