@@ -76,13 +76,18 @@ def test_unscaled_frames_copy_with_compose(ctx):
 
 
 @pytest.mark.parametrize("kind,iw,ih,ow,oh", [("alpha", 3840, 2160, 337, 190), ("noisea", 1000, 300, 37, 190),
-                                               ("photo", 1920, 360, 170, 100)])
-def test_two_pass_staged_first_pass_equals_plain(ctx, monkeypatch, kind, iw, ih, ow, oh):
+                                               ("photo", 1920, 360, 170, 100), ("alpha", 640, 480, 67, 50),
+                                               ("noisea", 517, 211, 33, 41)])
+def test_two_pass_first_pass_variants_agree(ctx, monkeypatch, kind, iw, ih, ow, oh):
+    """The horizontal first pass of the two-pass scaler has three thread mappings (staged through shared memory for mostly
+    full 32-column tiles, flat (row, column) pairs for few output columns, the plain tiled one): same bits, the oracle's."""
     src = synth.frame_np(77, iw, ih, kind)
     if kind == "noisea":
         src[::3, ::5, 3] = 0                                   # holes: the un-weighted (plain) passes run too
-    staged = ctx.scale(src, ow, oh)
+    default = ctx.scale(src, ow, oh)
     monkeypatch.setenv("B200TIMG_NO_H1S", "1")
+    no_staged = ctx.scale(src, ow, oh)
+    monkeypatch.setenv("B200TIMG_NO_H1F", "1")
     plain = ctx.scale(src, ow, oh)
-    assert (staged == plain).all()
-    assert (staged == oracle.stb_resize(src, ow, oh)).all()
+    assert (default == plain).all() and (no_staged == plain).all()
+    assert (plain == oracle.stb_resize(src, ow, oh)).all()

@@ -890,6 +890,34 @@ twopass_h1_kernel(const uint32_t *__restrict__ in, TwoPassParams T) {
     }
     T.tmp[((long long)f * P.ih + y) * P.ow + ox] = r;
 }
+// pass 1, horizontal first, FLAT: the same sums as twopass_h1_kernel with the (row, output column) pairs of `rows` source rows
+// laid out flat over the CTA's threads -- with few output columns (C1: 67 = two full 32-column tiles and one of 3) the tiled
+// mapping leaves 30 % of the lanes idle; here a CTA's rows x ow outputs fill its 256 threads to within a few per cent.
+template <bool PLAIN>
+__global__ void __launch_bounds__(256)
+twopass_h1f_kernel(const uint32_t *__restrict__ in, TwoPassParams T, int rows) {
+    const ResampleParams &P = T.P;
+    const int f = blockIdx.y, y0 = blockIdx.x * rows;
+    if (PLAIN && !T.need_plain[f]) return;
+    const int n = min(rows, P.ih - y0) * P.ow;
+    for (int idx = threadIdx.x; idx < n; idx += 256) {
+        const int ry = idx / P.ow, ox = idx - ry * P.ow, y = y0 + ry;
+        const uint32_t *row = in + (long long)f * P.iw * P.ih + (long long)y * P.iw + P.h_first[ox];
+        const float *hc = P.h_coeff + (long long)ox * P.h_widest;
+        const int cnt = P.h_count[ox];
+        float4 r;
+        if (P.h_sequential) {
+            r = mul4(decode_tp<PLAIN>(row[0], P.bgra), hc[0]);
+            for (int i = 1; i < cnt; ++i) r = add4(r, mul4(decode_tp<PLAIN>(row[i], P.bgra), hc[i]));
+        } else {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 a0 = z, a1 = z;
+            for (int i = 0; i < cnt; ++i) { const float4 t = mul4(decode_tp<PLAIN>(row[i], P.bgra), hc[i]); if (i & 1) a1 = add4(a1, t); else a0 = add4(a0, t); }
+            r = add4(a0, a1);
+        }
+        T.tmp[((long long)f * P.ih + y) * P.ow + ox] = r;
+    }
+}
 // pass 1, horizontal first, STAGED: the same sums as twopass_h1_kernel, but a warp decodes the stretch of its source row
 // that the CTA's 32 output columns need ONCE into shared memory (coalesced 128-byte loads) and the taps then read
 // float4s from there -- the plain kernel decodes every source pixel once per output that uses it (~4x for the long
@@ -1608,6 +1636,16 @@ int launch_scale(b200timg_ctx *ctx, const uint8_t *d_in, int iw, int ih, int fmt
                             B2_CUDA(ctx, cudaFuncSetAttribute(twopass_h1s_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
                             twopass_h1s_kernel<false><<<g1, 256, h1smem, ctx->stream>>>(in, T, HG);
                         }
+                    } else if (!tiles_full && ow <= 4096 && n_frames <= 65535 && !getenv("B200TIMG_NO_H1F")) {
+                        // few output columns: flat (row, column) mapping; rows per CTA chosen so that rows x ow fills whole 256-thread rounds
+                        int rows = 8; double best = 0.0;
+                        for (int r = 4; r <= 64; ++r) {
+                            const long long items = (long long)r * ow, slots = (items + 255) / 256 * 256;
+                            const double fill = (double)items / (double)slots;
+                            if (fill > best + 1e-9) { best = fill; rows = r; }
+                        }
+                        const dim3 gf((ih + rows - 1) / rows, n_frames);
+                        if (plain) twopass_h1f_kernel<true><<<gf, 256, 0, ctx->stream>>>(in, T, rows); else twopass_h1f_kernel<false><<<gf, 256, 0, ctx->stream>>>(in, T, rows);
                     } else if (plain) twopass_h1_kernel<true><<<g1, 256, 0, ctx->stream>>>(in, T); else twopass_h1_kernel<false><<<g1, 256, 0, ctx->stream>>>(in, T);
                     B2_LAUNCH_CHECK(ctx);
                     B2_KERNEL(ctx, plain ? "twopass_plain_kernels" : "twopass_2_kernel");
